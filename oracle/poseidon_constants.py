@@ -1,0 +1,106 @@
+"""Regenerates the Poseidon round constants and MDS matrices used by poseidon-rs 0.0.8.
+
+TEST INFRASTRUCTURE + BUILD-TIME GENERATOR.  Nothing here runs on the product's data path: the
+constants it produces are baked into a generated header (csrc/generated/poseidon_consts.inc) at
+build time, exactly as poseidon-rs bakes circomlib's `poseidon_constants` into its source.
+
+The reference crate calls `Poseidon::new()` / `POSEIDON.hash(..)` (reference src/lib.rs:59,
+:333, :370, :401).  poseidon-rs 0.0.8 (Cargo.toml:20) is NOT under /root/reference, so its
+constant tables are regenerated here from the published algorithm: the Poseidon authors'
+Grain-LFSR script with field=1 (prime), sbox=0 (x^alpha), n=254, t, R_F=8, R_P(t)  (SURVEY.md
+App. B).  Correctness is pinned by (i) the anchor constants below and (ii) the reference's own
+known-answer test `test_circomlib_testvector` (src/lib.rs:688-738), whose signature S depends on
+one full t=6 evaluation.
+"""
+
+Q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+R_F = 8
+R_P_TABLE = [56, 57, 56, 60, 60, 63, 64, 63]  # indexed by t-2, t = 2..9
+FIELD_BITS = 254
+
+
+class _Grain:
+    """80-bit Grain LFSR in self-shrinking mode, as specified in the Poseidon paper (App. F)."""
+
+    def __init__(self, t, r_f, r_p, n=FIELD_BITS, field=1, sbox=0):
+        bits = []
+        for value, width in ((field, 2), (sbox, 4), (n, 12), (t, 12), (r_f, 10), (r_p, 10)):
+            bits += [(value >> (width - 1 - i)) & 1 for i in range(width)]
+        bits += [1] * 30
+        assert len(bits) == 80
+        self.s = bits
+        for _ in range(160):
+            self._step()
+
+    def _step(self):
+        s = self.s
+        b = s[62] ^ s[51] ^ s[38] ^ s[23] ^ s[13] ^ s[0]
+        s.pop(0)
+        s.append(b)
+        return b
+
+    def bit(self):
+        b = self._step()
+        while b == 0:
+            self._step()          # discarded
+            b = self._step()
+        return self._step()
+
+    def integer(self, nbits=FIELD_BITS):
+        v = 0
+        for _ in range(nbits):
+            v = (v << 1) | self.bit()
+        return v
+
+
+def generate(t):
+    """Return (C, M): C = list of (R_F+R_P)*t round constants, M = t x t MDS matrix (ints mod Q)."""
+    assert 2 <= t <= 9
+    r_p = R_P_TABLE[t - 2]
+    g = _Grain(t, R_F, r_p)
+    consts = []
+    while len(consts) < (R_F + r_p) * t:
+        v = g.integer()
+        if v < Q:                      # rejection sampling for round constants
+            consts.append(v)
+    while True:
+        xy = [g.integer() % Q for _ in range(2 * t)]   # MDS seeds are reduced, not rejected
+        if len(set(xy)) != 2 * t:
+            continue
+        xs, ys = xy[:t], xy[t:]
+        if any((x + y) % Q == 0 for x in xs for y in ys):
+            continue
+        M = [[pow((xs[i] + ys[j]) % Q, Q - 2, Q) for j in range(t)] for i in range(t)]
+        return consts, M
+
+
+# Anchors (these equal circomlib's poseidon_constants.json entries).
+ANCHORS = {
+    2: {"C0": 0x09c46e9ec68e9bd4fe1faaba294cba38a71aa177534cdd1b6c7dc0dbd0abd7a7},
+    3: {"C0": 0x0ee9a592ba9a9518d05986d656f40c2114c4993c11bb29938d21d47304cd8e6e,
+        "M00": 0x109b7f411ba0e4c9b2b70caf5c36a7b194be7c11ad24378bfedb68592ba8118b},
+    6: {"C0": 0x1448614598e00f98e7ae7dea45fbd83bd968653ef8390cde2e86b706ad40c651,
+        "Clast": 0x16d87a5183a316a1d70afc951efe2cd667c77328fcfda458cbf5fe3045f46d9e,
+        "M00": 0x124666f80561ed5916f2f070b1bd248c6d53f44d273d956a0c87b917692a4d18,
+        "Mlast": 0x1b121c049cd1159e289007e0c9da9995cc4bab4c26fb888ec3972a8a2e656964},
+}
+
+_cache = {}
+
+
+def constants(t):
+    if t not in _cache:
+        C, M = generate(t)
+        a = ANCHORS.get(t, {})
+        assert a.get("C0", C[0]) == C[0], "Poseidon C[0] anchor mismatch for t=%d" % t
+        assert a.get("Clast", C[-1]) == C[-1], "Poseidon C[-1] anchor mismatch for t=%d" % t
+        assert a.get("M00", M[0][0]) == M[0][0], "Poseidon M[0][0] anchor mismatch for t=%d" % t
+        assert a.get("Mlast", M[-1][-1]) == M[-1][-1], "Poseidon M[-1][-1] anchor mismatch for t=%d" % t
+        _cache[t] = (C, M)
+    return _cache[t]
+
+
+if __name__ == "__main__":
+    for t in range(2, 10):
+        C, M = constants(t)
+        print("t=%d  R_P=%d  |C|=%d  C[0]=%#066x  M[0][0]=%#066x" % (t, R_P_TABLE[t - 2], len(C), C[0], M[0][0]))
