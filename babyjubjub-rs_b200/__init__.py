@@ -1,0 +1,367 @@
+"""babyjubjub-rs_b200: B200-native batch engine for babyjubjub-rs's hot path (host-side mirror).
+
+The reference is a Rust crate and there is no Rust toolchain in this image, so the host side above
+the C ABI (include/bjj_cuda.h, libbjj_cuda.so) is mirrored twice: `host/bjj.hpp` (C++, header-only)
+and this Python module, which the parity tests drive.  Names, argument meaning and error behaviour
+follow the reference's public API (paths into the reference tree):
+
+    Point{x,y}.projective/mul_scalar/compress/equals      src/lib.rs:134-186
+    PointProjective{x,y,z}.affine/add                      src/lib.rs:62-132
+    decompress_point, decompress_signature                 src/lib.rs:192-224, 260-268
+    Signature{r_b8,s}.compress                             src/lib.rs:239-258
+    PrivateKey{key}.scalar_key/public                      src/lib.rs:270-306
+    verify(pk, sig, msg)                                   src/lib.rs:395-412
+    + the batch entry points the north star adds: mul_scalar_batch, public_batch,
+      decompress_batch, verify_batch (and add/compress/poseidon/fixed-base batches).
+
+Every call runs on the GPU through libbjj_cuda.so; there is no CPU fallback -- importing works
+without a GPU (so the ABI can be inspected), creating an Engine does not.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import BjjError
+
+Q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+ORDER = 21888242871839275222246405745257275088614511777268538073601725287587578984328
+SUBORDER = ORDER >> 3
+B8 = (5299619240641551281634865583518297030282874472190772894086521144482721001553,
+      16950150798460657717958625567821834550301663161624707787222815936182638968203)
+
+FR_MUL, FR_ADD, FR_SUB, FR_INV, FR_SQR = 0, 1, 2, 3, 4
+STATUS_STRINGS = {
+    0: "",
+    1: "y outside the Finite Field over R",
+    2: "no mod inv of Zero",
+    3: "not a mod p square",
+    4: "msg outside the Finite Field",
+}
+ERR_NONCANONICAL = 3
+
+
+# ---- conversions ---------------------------------------------------------------------------------
+def ints_to_le32(values):
+    """list of non-negative ints < 2^256 -> uint8 array (n, 32), little-endian."""
+    buf = b"".join(int(v).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint8).reshape(-1, 32).copy()
+
+
+def le32_to_ints(arr):
+    raw = np.ascontiguousarray(arr, dtype=np.uint8).tobytes()
+    return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
+
+
+def _as_u8(a, width):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 1:
+        a = a.reshape(-1, width)
+    if a.ndim != 2 or a.shape[1] != width:
+        raise ValueError("expected uint8 array of shape (n, %d), got %r" % (width, a.shape))
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """One bjj_ctx on one device (one host thread, one stream; no NCCL -- nothing is exchanged)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        if self.lib.bjj_device_count() < 1:
+            raise RuntimeError("babyjubjub-rs_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        ctx = ctypes.c_void_p()
+        rc = self.lib.bjj_init(int(device), ctypes.byref(ctx))
+        if rc != 0:
+            raise BjjError(rc, "bjj_init", self.lib.bjj_error_string(rc).decode())
+        self.ctx = ctx
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.bjj_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def _check(self, rc, what, allow_noncanonical=False):
+        if rc == 0 or (allow_noncanonical and rc == ERR_NONCANONICAL):
+            return rc
+        detail = self.lib.bjj_error_string(rc).decode()
+        if rc == 1:
+            detail += ": " + self.lib.bjj_last_cuda_error(self.ctx).decode()
+        raise BjjError(rc, what, detail)
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.bjj_kernel_launches(self.ctx))
+
+    @property
+    def stream(self):
+        return self.lib.bjj_stream(self.ctx)
+
+    def sync(self):
+        return self._check(self.lib.bjj_sync(self.ctx), "bjj_sync")
+
+    # -- batch ops on (n, 32) uint8 arrays (host memory)
+    def fr_op_batch(self, op, a, b=None):
+        a = _as_u8(a, 32)
+        b = a if b is None else _as_u8(b, 32)
+        out = np.empty_like(a)
+        self._check(self.lib.bjj_fr_op_batch(self.ctx, op, len(a), _ptr(a), _ptr(b), _ptr(out)), "bjj_fr_op_batch")
+        return out
+
+    def add_batch(self, px, py, pz, qx, qy, qz):
+        ins = [_as_u8(v, 32) for v in (px, py, pz, qx, qy, qz)]
+        outs = [np.empty_like(ins[0]) for _ in range(3)]
+        self._check(self.lib.bjj_add_batch(self.ctx, len(ins[0]), *[_ptr(v) for v in ins + outs]), "bjj_add_batch")
+        return tuple(outs)
+
+    def affine_batch(self, px, py, pz):
+        ins = [_as_u8(v, 32) for v in (px, py, pz)]
+        outs = [np.empty_like(ins[0]) for _ in range(2)]
+        self._check(self.lib.bjj_affine_batch(self.ctx, len(ins[0]), *[_ptr(v) for v in ins + outs]), "bjj_affine_batch")
+        return tuple(outs)
+
+    def mul_scalar_batch(self, px, py, scalars):
+        ins = [_as_u8(v, 32) for v in (px, py, scalars)]
+        outs = [np.empty_like(ins[0]) for _ in range(2)]
+        self._check(self.lib.bjj_mul_scalar_batch(self.ctx, len(ins[0]), *[_ptr(v) for v in ins + outs]),
+                    "bjj_mul_scalar_batch")
+        return tuple(outs)
+
+    def fixed_base_batch(self, scalars):
+        k = _as_u8(scalars, 32)
+        outs = [np.empty_like(k) for _ in range(2)]
+        self._check(self.lib.bjj_fixed_base_batch(self.ctx, len(k), _ptr(k), _ptr(outs[0]), _ptr(outs[1])),
+                    "bjj_fixed_base_batch")
+        return tuple(outs)
+
+    def public_batch(self, keys):
+        k = _as_u8(keys, 32)
+        outs = [np.empty_like(k) for _ in range(2)]
+        self._check(self.lib.bjj_public_batch(self.ctx, len(k), _ptr(k), _ptr(outs[0]), _ptr(outs[1])), "bjj_public_batch")
+        return tuple(outs)
+
+    def scalar_key_batch(self, keys):
+        k = _as_u8(keys, 32)
+        out = np.empty_like(k)
+        self._check(self.lib.bjj_scalar_key_batch(self.ctx, len(k), _ptr(k), _ptr(out)), "bjj_scalar_key_batch")
+        return out
+
+    def sign_batch(self, keys, msgs):
+        k, m = _as_u8(keys, 32), _as_u8(msgs, 32)
+        rx, ry, s = (np.empty_like(k) for _ in range(3))
+        status = np.empty(len(k), dtype=np.uint8)
+        self._check(self.lib.bjj_sign_batch(self.ctx, len(k), _ptr(k), _ptr(m), _ptr(rx), _ptr(ry), _ptr(s), _ptr(status)),
+                    "bjj_sign_batch")
+        return rx, ry, s, status
+
+    def compress_batch(self, px, py):
+        x, y = _as_u8(px, 32), _as_u8(py, 32)
+        out = np.empty_like(x)
+        self._check(self.lib.bjj_compress_batch(self.ctx, len(x), _ptr(x), _ptr(y), _ptr(out)), "bjj_compress_batch")
+        return out
+
+    def decompress_batch(self, comp):
+        c = _as_u8(comp, 32)
+        rx, ry = np.empty_like(c), np.empty_like(c)
+        status = np.empty(len(c), dtype=np.uint8)
+        self._check(self.lib.bjj_decompress_batch(self.ctx, len(c), _ptr(c), _ptr(rx), _ptr(ry), _ptr(status)),
+                    "bjj_decompress_batch")
+        return rx, ry, status
+
+    def poseidon_batch(self, inputs):
+        ins = [_as_u8(v, 32) for v in inputs]
+        if not 1 <= len(ins) <= 8:
+            raise ValueError("invalid inputs length")       # poseidon-rs: Err on 0 or > 8 inputs
+        arr = (ctypes.c_void_p * len(ins))(*[v.ctypes.data for v in ins])
+        out = np.empty_like(ins[0])
+        self._check(self.lib.bjj_poseidon_batch(self.ctx, len(ins), len(ins[0]), arr, _ptr(out)), "bjj_poseidon_batch")
+        return out
+
+    def verify_batch(self, r8x, r8y, s, ax, ay, msg):
+        ins = [_as_u8(v, 32) for v in (r8x, r8y, s, ax, ay, msg)]
+        ok = np.empty(len(ins[0]), dtype=np.uint8)
+        self._check(self.lib.bjj_verify_batch(self.ctx, len(ins[0]), *[_ptr(v) for v in ins], _ptr(ok)), "bjj_verify_batch")
+        return ok
+
+    def verify_compressed_batch(self, sig64, pk32, msg):
+        sg, pk, m = _as_u8(sig64, 64), _as_u8(pk32, 32), _as_u8(msg, 32)
+        ok = np.empty(len(sg), dtype=np.uint8)
+        status = np.empty(len(sg), dtype=np.uint8)
+        self._check(self.lib.bjj_verify_compressed_batch(self.ctx, len(sg), _ptr(sg), _ptr(pk), _ptr(m), _ptr(ok), _ptr(status)),
+                    "bjj_verify_compressed_batch")
+        return ok, status
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+# ---- the reference's public API, as batches of one -------------------------------------------------
+class PointProjective:
+    """src/lib.rs:62-132"""
+
+    def __init__(self, x, y, z):
+        self.x, self.y, self.z = int(x), int(y), int(z)
+
+    def affine(self):
+        rx, ry = default_engine().affine_batch(*[ints_to_le32([v]) for v in (self.x, self.y, self.z)])
+        return Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0])
+
+    def add(self, q):
+        outs = default_engine().add_batch(*[ints_to_le32([v]) for v in (self.x, self.y, self.z, q.x, q.y, q.z)])
+        return PointProjective(*[le32_to_ints(o)[0] for o in outs])
+
+
+class Point:
+    """src/lib.rs:134-186"""
+
+    def __init__(self, x, y):
+        self.x, self.y = int(x), int(y)
+
+    def projective(self):
+        return PointProjective(self.x, self.y, 1)
+
+    def mul_scalar(self, n):
+        n = abs(int(n))                                  # src/lib.rs:156 drops the sign
+        if n >> 256:
+            raise ValueError("scalar wider than 256 bits: reduce on the host (mod ORDER, on-curve points only)")
+        rx, ry = default_engine().mul_scalar_batch(ints_to_le32([self.x]), ints_to_le32([self.y]), ints_to_le32([n]))
+        return Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0])
+
+    def compress(self):
+        return default_engine().compress_batch(ints_to_le32([self.x]), ints_to_le32([self.y])).tobytes()
+
+    def equals(self, p):
+        return self.x == p.x and self.y == p.y
+
+    def __eq__(self, other):
+        return isinstance(other, Point) and self.equals(other)
+
+    def __repr__(self):
+        return "Point(x=Fr(0x%064x), y=Fr(0x%064x))" % (self.x, self.y)
+
+
+def decompress_point(bb):
+    """src/lib.rs:192-224; raises ValueError(<the reference's Err string>)."""
+    if len(bb) != 32:
+        raise ValueError("expected 32 bytes")
+    rx, ry, st = default_engine().decompress_batch(np.frombuffer(bytes(bb), dtype=np.uint8).reshape(1, 32))
+    if st[0]:
+        raise ValueError(STATUS_STRINGS[int(st[0])])
+    return Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0])
+
+
+class Signature:
+    """src/lib.rs:239-258"""
+
+    def __init__(self, r_b8, s):
+        self.r_b8, self.s = r_b8, int(s)
+
+    def compress(self):
+        return self.r_b8.compress() + (self.s & ((1 << 256) - 1)).to_bytes(32, "little")
+
+
+def decompress_signature(b):
+    """src/lib.rs:260-268"""
+    if len(b) != 64:
+        raise ValueError("expected 64 bytes")
+    return Signature(decompress_point(b[:32]), int.from_bytes(b[32:], "little"))
+
+
+class PrivateKey:
+    """src/lib.rs:270-342 (import, scalar_key, public, sign)."""
+
+    def __init__(self, key):
+        self.key = bytes(key)
+
+    @staticmethod
+    def import_(b):
+        if len(b) != 32:
+            raise ValueError("imported key can not be bigger than 32 bytes")       # src/lib.rs:277
+        return PrivateKey(b)
+
+    def scalar_key(self):
+        out = default_engine().scalar_key_batch(np.frombuffer(self.key, dtype=np.uint8).reshape(1, 32))
+        return le32_to_ints(out)[0]
+
+    def public(self):
+        rx, ry = default_engine().public_batch(np.frombuffer(self.key, dtype=np.uint8).reshape(1, 32))
+        return Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0])
+
+
+def _sign(self, msg):
+    """PrivateKey::sign, src/lib.rs:308-342; raises ValueError("msg outside the Finite Field")."""
+    msg = int(msg)
+    if msg > Q:
+        raise ValueError(STATUS_STRINGS[4])
+    rx, ry, s, st = default_engine().sign_batch(np.frombuffer(self.key, dtype=np.uint8).reshape(1, 32), ints_to_le32([msg]))
+    if st[0]:
+        raise ValueError(STATUS_STRINGS[int(st[0])])
+    return Signature(Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0]), le32_to_ints(s)[0])
+
+
+PrivateKey.sign = _sign
+
+
+def verify(pk, sig, msg):
+    """src/lib.rs:395-412"""
+    msg = int(msg)
+    if msg > Q:
+        return False
+    if msg < 0:
+        raise ValueError("negative msg (the reference panics in Fr::from_str)")
+    if sig.s >> 256:
+        raise ValueError("S wider than 256 bits")
+    eng = default_engine()
+    ok = eng.verify_batch(*[ints_to_le32([v]) for v in (sig.r_b8.x, sig.r_b8.y, sig.s, pk.x, pk.y, msg)])
+    return bool(ok[0])
+
+
+# ---- batch entry points named by the north star ------------------------------------------------------
+def mul_scalar_batch(points, scalars, engine=None):
+    eng = engine or default_engine()
+    rx, ry = eng.mul_scalar_batch(ints_to_le32([p.x for p in points]), ints_to_le32([p.y for p in points]),
+                                  ints_to_le32([abs(int(k)) for k in scalars]))
+    return [Point(x, y) for x, y in zip(le32_to_ints(rx), le32_to_ints(ry))]
+
+
+def public_batch(keys, engine=None):
+    eng = engine or default_engine()
+    rx, ry = eng.public_batch(np.frombuffer(b"".join(bytes(k.key if isinstance(k, PrivateKey) else k) for k in keys),
+                                            dtype=np.uint8).reshape(-1, 32))
+    return [Point(x, y) for x, y in zip(le32_to_ints(rx), le32_to_ints(ry))]
+
+
+def decompress_batch(blobs, engine=None):
+    """-> list of Point or ValueError instances (the reference returns Result<Point, String>)."""
+    eng = engine or default_engine()
+    rx, ry, st = eng.decompress_batch(np.frombuffer(b"".join(bytes(b) for b in blobs), dtype=np.uint8).reshape(-1, 32))
+    xs, ys = le32_to_ints(rx), le32_to_ints(ry)
+    return [Point(x, y) if s == 0 else ValueError(STATUS_STRINGS[int(s)]) for x, y, s in zip(xs, ys, st)]
+
+
+def verify_batch(pks, sigs, msgs, engine=None):
+    eng = engine or default_engine()
+    # msg > Q is `false` in the reference; clamp such messages to an all-ones word (still > Q) so they fit 32 bytes
+    mm = [int(m) if int(m) <= Q else (1 << 256) - 1 for m in msgs]
+    ok = eng.verify_batch(ints_to_le32([s.r_b8.x for s in sigs]), ints_to_le32([s.r_b8.y for s in sigs]),
+                          ints_to_le32([s.s for s in sigs]), ints_to_le32([p.x for p in pks]),
+                          ints_to_le32([p.y for p in pks]), ints_to_le32(mm))
+    return [bool(v) for v in ok]

@@ -1,0 +1,687 @@
+// libbjj_cuda: kernels + C ABI (include/bjj_cuda.h).  sm_100a only; no CPU fallback.
+//
+// Kernel shape: one lane per thread, 128-thread CTAs, grid = min(ceil(n/128), SMs x resident CTAs)
+// with a grid-stride loop, so every launch is a whole number of waves on the 148 SMs.  The work is
+// bound by the integer-multiply (fma) pipe, not by HBM: a lane reads <= 192 B and executes ~10^5-10^6
+// instructions.  Loads are two 16-byte vector loads per 32-byte element (1 KiB contiguous per warp).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/bjj_cuda.h"
+#include "lanes.cuh"
+
+using namespace bjj;
+
+#define BJJ_BLOCK 128
+#define BJJ_PIPE_SLOTS 2
+#define BJJ_CHUNK_LANES (1u << 20)
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+#define BJJ_LANE_LOOP(n) \
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+#define BJJ_FLAGS_BEGIN uint32_t flags = 0;
+#define BJJ_FLAGS_END(p) \
+    if (flags) atomicOr(p, flags);
+
+__device__ __forceinline__ LaneTable thread_table(U128* base) {
+    LaneTable t;
+    t.base = base;
+    t.stride = (size_t)gridDim.x * blockDim.x;
+    t.slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    return t;
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_comb_build(CombEntry* comb) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES) return;
+    int w = idx / BJJ_COMB_ENTRIES, j = idx % BJJ_COMB_ENTRIES;
+    if (w == 32 && j > 1) return;
+    comb_build_entry(comb, w, j);
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_fr_op(int op, size_t n, const uint8_t* a, const uint8_t* b,
+                                                     uint8_t* out, uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    BJJ_LANE_LOOP(n) lane_fr_op(op, a, b, out, i, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_add(size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz,
+                                                   const uint8_t* qx, const uint8_t* qy, const uint8_t* qz,
+                                                   uint8_t* rx, uint8_t* ry, uint8_t* rz, uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    BJJ_LANE_LOOP(n) lane_add(px, py, pz, qx, qy, qz, rx, ry, rz, i, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_affine(size_t n, const uint8_t* px, const uint8_t* py,
+                                                      const uint8_t* pz, uint8_t* rx, uint8_t* ry, uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    BJJ_LANE_LOOP(n) lane_affine(px, py, pz, rx, ry, i, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py,
+                                                          const uint8_t* k, uint8_t* rx, uint8_t* ry, U128* table,
+                                                          uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    const LaneTable tbl = thread_table(table);
+    BJJ_LANE_LOOP(n) lane_mul_scalar(px, py, k, rx, ry, i, tbl, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_fixed_base(size_t n, const uint8_t* k, uint8_t* rx, uint8_t* ry,
+                                                          const CombEntry* comb) {
+    BJJ_LANE_LOOP(n) lane_fixed_base(k, rx, ry, i, comb);
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_public(size_t n, const uint8_t* key, uint8_t* rx, uint8_t* ry,
+                                                      const CombEntry* comb) {
+    BJJ_LANE_LOOP(n) lane_public(key, rx, ry, i, comb);
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_sign(size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* r8x,
+                                                    uint8_t* r8y, uint8_t* s32, uint8_t* status, const CombEntry* comb) {
+    BJJ_LANE_LOOP(n) lane_sign(key, msg, r8x, r8y, s32, status, i, comb);
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_scalar_key(size_t n, const uint8_t* key, uint8_t* out) {
+    BJJ_LANE_LOOP(n) lane_scalar_key(key, out, i);
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_compress(size_t n, const uint8_t* px, const uint8_t* py, uint8_t* out,
+                                                        uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    BJJ_LANE_LOOP(n) lane_compress(px, py, out, i, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress(size_t n, const uint8_t* in, uint8_t* rx, uint8_t* ry,
+                                                          uint8_t* status) {
+    BJJ_LANE_LOOP(n) lane_decompress(in, rx, ry, status, i);
+}
+
+struct PoseidonIn {
+    const uint8_t* p[8];
+};
+template <int T>
+__global__ void __launch_bounds__(BJJ_BLOCK) k_poseidon(size_t n, PoseidonIn in, uint8_t* out, uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    BJJ_LANE_LOOP(n) lane_poseidon<T>(in.p, out, i, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+                                                      const uint8_t* s, const uint8_t* ax, const uint8_t* ay,
+                                                      const uint8_t* msg, uint8_t* ok, U128* table,
+                                                      const CombEntry* comb, uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    const LaneTable tbl = thread_table(table);
+    BJJ_LANE_LOOP(n) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, tbl, comb, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32,
+                                                                 const uint8_t* msg, uint8_t* ok, uint8_t* status,
+                                                                 U128* table, const CombEntry* comb) {
+    const LaneTable tbl = thread_table(table);
+    BJJ_LANE_LOOP(n) lane_verify_compressed(sig64, pk32, msg, ok, status, i, tbl, comb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct PipeSlot {
+    cudaStream_t stream;
+    uint8_t* arena;
+    size_t arena_bytes;
+    U128* table;
+    size_t table_slots;
+};
+
+struct bjj_ctx {
+    int device;
+    int sms;
+    cudaStream_t stream;        // stream of the _dev flavour when the caller passes NULL
+    CombEntry* comb;
+    U128* table;                // per-thread window tables of the _dev flavour
+    size_t table_slots;
+    uint32_t* flags_dev;
+    uint32_t* flags_host;       // pinned
+    PipeSlot slot[BJJ_PIPE_SLOTS];
+    unsigned long long launches;
+    cudaError_t last;
+};
+
+#define CU(ctx, call)                      \
+    do {                                   \
+        cudaError_t e_ = (call);           \
+        if (e_ != cudaSuccess) {           \
+            (ctx)->last = e_;              \
+            return BJJ_ERR_CUDA;           \
+        }                                  \
+    } while (0)
+
+static int grid_for(bjj_ctx* ctx, const void* kernel, size_t n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BJJ_BLOCK, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    size_t want = (n + BJJ_BLOCK - 1) / BJJ_BLOCK;
+    size_t cap = (size_t)ctx->sms * per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+static int ensure_table(bjj_ctx* ctx, U128** table, size_t* have, size_t slots) {
+    if (*have >= slots) return BJJ_OK;
+    if (*table) cudaFree(*table);
+    *table = nullptr;
+    *have = 0;
+    CU(ctx, cudaMalloc(table, slots * BJJ_TABLE_U128_PER_LANE * sizeof(U128)));
+    *have = slots;
+    return BJJ_OK;
+}
+
+extern "C" {
+
+int bjj_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* bjj_error_string(int code) {
+    switch (code) {
+        case BJJ_OK: return "ok";
+        case BJJ_ERR_CUDA: return "CUDA runtime error";
+        case BJJ_ERR_ARG: return "invalid argument";
+        case BJJ_ERR_NONCANONICAL: return "field element input >= Q (results computed mod Q)";
+        case BJJ_ERR_NOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+const char* bjj_status_string(int status) {
+    switch (status) {
+        case BJJ_STATUS_OK: return "";
+        case BJJ_STATUS_Y_RANGE: return "y outside the Finite Field over R";
+        case BJJ_STATUS_NO_INV: return "no mod inv of Zero";
+        case BJJ_STATUS_NOT_SQUARE: return "not a mod p square";
+        case BJJ_STATUS_MSG_RANGE: return "msg outside the Finite Field";
+        default: return "unknown status";
+    }
+}
+
+const char* bjj_last_cuda_error(bjj_ctx* ctx) { return ctx ? cudaGetErrorString(ctx->last) : "no context"; }
+void* bjj_stream(bjj_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int bjj_device(bjj_ctx* ctx) { return ctx ? ctx->device : -1; }
+unsigned long long bjj_kernel_launches(bjj_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* bjj_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void bjj_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+void* bjj_dev_alloc(bjj_ctx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    void* p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void bjj_dev_free(bjj_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+int bjj_memcpy_h2d(bjj_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return BJJ_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return BJJ_OK;
+}
+int bjj_memcpy_d2h(bjj_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return BJJ_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return BJJ_OK;
+}
+
+void bjj_destroy(bjj_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < BJJ_PIPE_SLOTS; s++) {
+        if (ctx->slot[s].arena) cudaFree(ctx->slot[s].arena);
+        if (ctx->slot[s].table) cudaFree(ctx->slot[s].table);
+        if (ctx->slot[s].stream) cudaStreamDestroy(ctx->slot[s].stream);
+    }
+    if (ctx->table) cudaFree(ctx->table);
+    if (ctx->comb) cudaFree(ctx->comb);
+    if (ctx->flags_dev) cudaFree(ctx->flags_dev);
+    if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+int bjj_init(int device, bjj_ctx** out) {
+    if (!out) return BJJ_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return BJJ_ERR_CUDA;
+    bjj_ctx* ctx = (bjj_ctx*)calloc(1, sizeof(bjj_ctx));
+    if (!ctx) return BJJ_ERR_NOMEM;
+    ctx->device = device;
+    ctx->last = cudaSuccess;
+#define INIT_CU(call)                  \
+    do {                               \
+        cudaError_t e_ = (call);       \
+        if (e_ != cudaSuccess) {       \
+            fprintf(stderr, "libbjj_cuda: %s failed: %s\n", #call, cudaGetErrorString(e_)); \
+            bjj_destroy(ctx);          \
+            return BJJ_ERR_CUDA;       \
+        }                              \
+    } while (0)
+    INIT_CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    INIT_CU(cudaGetDeviceProperties(&prop, device));
+    ctx->sms = prop.multiProcessorCount;
+    INIT_CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int s = 0; s < BJJ_PIPE_SLOTS; s++) INIT_CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
+    INIT_CU(cudaMalloc(&ctx->flags_dev, sizeof(uint32_t)));
+    INIT_CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(uint32_t), ctx->stream));
+    INIT_CU(cudaHostAlloc(&ctx->flags_host, sizeof(uint32_t), cudaHostAllocDefault));
+    const size_t comb_bytes = (size_t)BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES * sizeof(CombEntry);
+    INIT_CU(cudaMalloc(&ctx->comb, comb_bytes));
+    INIT_CU(cudaMemsetAsync(ctx->comb, 0, comb_bytes, ctx->stream));
+    const int total = BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES;
+    k_comb_build<<<(total + BJJ_BLOCK - 1) / BJJ_BLOCK, BJJ_BLOCK, 0, ctx->stream>>>(ctx->comb);
+    ctx->launches++;
+    INIT_CU(cudaGetLastError());
+    INIT_CU(cudaStreamSynchronize(ctx->stream));
+#undef INIT_CU
+    *out = ctx;
+    return BJJ_OK;
+}
+
+// waits for the ctx stream and all pipeline slots; returns + clears the sticky error flags
+int bjj_sync(bjj_ctx* ctx) {
+    if (!ctx) return BJJ_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int s = 0; s < BJJ_PIPE_SLOTS; s++) CU(ctx, cudaStreamSynchronize(ctx->slot[s].stream));
+    CU(ctx, cudaMemcpyAsync(ctx->flags_host, ctx->flags_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->flags_dev, 0, sizeof(uint32_t), ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t f = *ctx->flags_host;
+    if (f & BJJ_FLAG_NONCANONICAL) return BJJ_ERR_NONCANONICAL;
+    return BJJ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// device-pointer flavour: one launch per call
+// ---------------------------------------------------------------------------------------------------
+#define DEV_PROLOGUE                                         \
+    if (!ctx) return BJJ_ERR_ARG;                            \
+    if (n == 0) return BJJ_OK;                               \
+    CU(ctx, cudaSetDevice(ctx->device));                     \
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+#define DEV_EPILOGUE              \
+    ctx->launches++;              \
+    CU(ctx, cudaGetLastError()); \
+    return BJJ_OK;
+
+// `table`/`table_slots` select the per-thread window-table workspace (ctx-wide for _dev calls, per
+// pipeline slot for host calls).
+static int launch_mul_scalar(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
+                             uint8_t* rx, uint8_t* ry, cudaStream_t st, U128** table, size_t* slots) {
+    int grid = grid_for(ctx, (const void*)k_mul_scalar, n);
+    int rc = ensure_table(ctx, table, slots, (size_t)grid * BJJ_BLOCK);
+    if (rc) return rc;
+    k_mul_scalar<<<grid, BJJ_BLOCK, 0, st>>>(n, px, py, k, rx, ry, *table, ctx->flags_dev);
+    DEV_EPILOGUE
+}
+static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
+                         const uint8_t* ax, const uint8_t* ay, const uint8_t* msg, uint8_t* ok, cudaStream_t st,
+                         U128** table, size_t* slots) {
+    int grid = grid_for(ctx, (const void*)k_verify, n);
+    int rc = ensure_table(ctx, table, slots, (size_t)grid * BJJ_BLOCK);
+    if (rc) return rc;
+    k_verify<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s, ax, ay, msg, ok, *table, ctx->comb, ctx->flags_dev);
+    DEV_EPILOGUE
+}
+static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
+                                    const uint8_t* msg, uint8_t* ok, uint8_t* status, cudaStream_t st, U128** table,
+                                    size_t* slots) {
+    int grid = grid_for(ctx, (const void*)k_verify_compressed, n);
+    int rc = ensure_table(ctx, table, slots, (size_t)grid * BJJ_BLOCK);
+    if (rc) return rc;
+    k_verify_compressed<<<grid, BJJ_BLOCK, 0, st>>>(n, sig64, pk32, msg, ok, status, *table, ctx->comb);
+    DEV_EPILOGUE
+}
+static int launch_poseidon(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out,
+                           cudaStream_t st) {
+    PoseidonIn pin;
+    for (int j = 0; j < 8; j++) pin.p[j] = j < n_inputs ? in[j] : nullptr;
+#define POS_CASE(T_)                                                                              \
+    case T_ - 1: {                                                                                \
+        int grid = grid_for(ctx, (const void*)k_poseidon<T_>, n);                                 \
+        k_poseidon<T_><<<grid, BJJ_BLOCK, 0, st>>>(n, pin, out, ctx->flags_dev);                  \
+        break;                                                                                    \
+    }
+    switch (n_inputs) {
+        POS_CASE(2)
+        POS_CASE(3)
+        POS_CASE(4)
+        POS_CASE(5)
+        POS_CASE(6)
+        POS_CASE(7)
+        POS_CASE(8)
+        POS_CASE(9)
+        default: return BJJ_ERR_ARG;
+    }
+#undef POS_CASE
+    DEV_EPILOGUE
+}
+
+extern "C" {
+
+int bjj_fr_op_batch_dev(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, void* stream) {
+    DEV_PROLOGUE
+    if (!a || !out || op < 0 || op > 4) return BJJ_ERR_ARG;
+    if (!b) b = a;
+    k_fr_op<<<grid_for(ctx, (const void*)k_fr_op, n), BJJ_BLOCK, 0, st>>>(op, n, a, b, out, ctx->flags_dev);
+    DEV_EPILOGUE
+}
+
+int bjj_add_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz,
+                      const uint8_t* qx, const uint8_t* qy, const uint8_t* qz, uint8_t* rx, uint8_t* ry, uint8_t* rz,
+                      void* stream) {
+    DEV_PROLOGUE
+    if (!px || !py || !pz || !qx || !qy || !qz || !rx || !ry || !rz) return BJJ_ERR_ARG;
+    k_add<<<grid_for(ctx, (const void*)k_add, n), BJJ_BLOCK, 0, st>>>(n, px, py, pz, qx, qy, qz, rx, ry, rz, ctx->flags_dev);
+    DEV_EPILOGUE
+}
+
+int bjj_affine_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz, uint8_t* rx,
+                         uint8_t* ry, void* stream) {
+    DEV_PROLOGUE
+    if (!px || !py || !pz || !rx || !ry) return BJJ_ERR_ARG;
+    k_affine<<<grid_for(ctx, (const void*)k_affine, n), BJJ_BLOCK, 0, st>>>(n, px, py, pz, rx, ry, ctx->flags_dev);
+    DEV_EPILOGUE
+}
+
+int bjj_mul_scalar_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar32,
+                             uint8_t* rx, uint8_t* ry, void* stream) {
+    DEV_PROLOGUE
+    if (!px || !py || !scalar32 || !rx || !ry) return BJJ_ERR_ARG;
+    return launch_mul_scalar(ctx, n, px, py, scalar32, rx, ry, st, &ctx->table, &ctx->table_slots);
+}
+
+int bjj_fixed_base_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry, void* stream) {
+    DEV_PROLOGUE
+    if (!scalar32 || !rx || !ry) return BJJ_ERR_ARG;
+    k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, n), BJJ_BLOCK, 0, st>>>(n, scalar32, rx, ry, ctx->comb);
+    DEV_EPILOGUE
+}
+
+int bjj_public_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* rx, uint8_t* ry, void* stream) {
+    DEV_PROLOGUE
+    if (!key32 || !rx || !ry) return BJJ_ERR_ARG;
+    k_public<<<grid_for(ctx, (const void*)k_public, n), BJJ_BLOCK, 0, st>>>(n, key32, rx, ry, ctx->comb);
+    DEV_EPILOGUE
+}
+
+int bjj_sign_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, uint8_t* r8y,
+                       uint8_t* s32, uint8_t* status, void* stream) {
+    DEV_PROLOGUE
+    if (!key32 || !msg32 || !r8x || !r8y || !s32 || !status) return BJJ_ERR_ARG;
+    k_sign<<<grid_for(ctx, (const void*)k_sign, n), BJJ_BLOCK, 0, st>>>(n, key32, msg32, r8x, r8y, s32, status, ctx->comb);
+    DEV_EPILOGUE
+}
+
+int bjj_scalar_key_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* scalar32, void* stream) {
+    DEV_PROLOGUE
+    if (!key32 || !scalar32) return BJJ_ERR_ARG;
+    k_scalar_key<<<grid_for(ctx, (const void*)k_scalar_key, n), BJJ_BLOCK, 0, st>>>(n, key32, scalar32);
+    DEV_EPILOGUE
+}
+
+int bjj_compress_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, uint8_t* out32, void* stream) {
+    DEV_PROLOGUE
+    if (!px || !py || !out32) return BJJ_ERR_ARG;
+    k_compress<<<grid_for(ctx, (const void*)k_compress, n), BJJ_BLOCK, 0, st>>>(n, px, py, out32, ctx->flags_dev);
+    DEV_EPILOGUE
+}
+
+int bjj_decompress_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* rx, uint8_t* ry, uint8_t* status,
+                             void* stream) {
+    DEV_PROLOGUE
+    if (!in32 || !rx || !ry || !status) return BJJ_ERR_ARG;
+    k_decompress<<<grid_for(ctx, (const void*)k_decompress, n), BJJ_BLOCK, 0, st>>>(n, in32, rx, ry, status);
+    DEV_EPILOGUE
+}
+
+int bjj_poseidon_batch_dev(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out, void* stream) {
+    DEV_PROLOGUE
+    if (!in || !out || n_inputs < 1 || n_inputs > 8) return BJJ_ERR_ARG;
+    for (int j = 0; j < n_inputs; j++)
+        if (!in[j]) return BJJ_ERR_ARG;
+    return launch_poseidon(ctx, n_inputs, n, in, out, st);
+}
+
+int bjj_verify_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32,
+                         const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, void* stream) {
+    DEV_PROLOGUE
+    if (!r8x || !r8y || !s32 || !ax || !ay || !msg32 || !ok) return BJJ_ERR_ARG;
+    return launch_verify(ctx, n, r8x, r8y, s32, ax, ay, msg32, ok, st, &ctx->table, &ctx->table_slots);
+}
+
+int bjj_verify_compressed_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
+                                    const uint8_t* msg32, uint8_t* ok, uint8_t* status, void* stream) {
+    DEV_PROLOGUE
+    if (!sig64 || !pk32 || !msg32 || !ok || !status) return BJJ_ERR_ARG;
+    return launch_verify_compressed(ctx, n, sig64, pk32, msg32, ok, status, st, &ctx->table, &ctx->table_slots);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// host-pointer flavour: chunked, double-buffered H2D -> kernel -> D2H pipeline over two streams
+// ---------------------------------------------------------------------------------------------------
+struct HostArg {
+    const uint8_t* in;    // non-null for inputs
+    uint8_t* out;         // non-null for outputs
+    size_t bytes_per_lane;
+};
+
+template <class Launch>
+static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch launch) {
+    if (!ctx) return BJJ_ERR_ARG;
+    for (int a = 0; a < nargs; a++)
+        if (!args[a].in && !args[a].out) return BJJ_ERR_ARG;
+    if (n == 0) return BJJ_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    size_t lane_bytes = 0;
+    for (int a = 0; a < nargs; a++) lane_bytes += (args[a].bytes_per_lane + 15) & ~(size_t)15;
+    const size_t chunk = n < BJJ_CHUNK_LANES ? n : BJJ_CHUNK_LANES;
+    // every array slice starts 256-byte aligned inside the arena
+    size_t need = 0;
+    for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * chunk + 255) & ~(size_t)255);
+    (void)lane_bytes;
+    int rc = BJJ_OK;
+    int which = 0;
+    for (size_t off = 0; off < n; off += chunk, which ^= 1) {
+        PipeSlot& sl = ctx->slot[which];
+        const size_t m = (n - off) < chunk ? (n - off) : chunk;
+        // the slot's previous chunk must have drained before its arena is reused
+        CU(ctx, cudaStreamSynchronize(sl.stream));
+        if (sl.arena_bytes < need) {
+            if (sl.arena) cudaFree(sl.arena);
+            sl.arena = nullptr;
+            sl.arena_bytes = 0;
+            CU(ctx, cudaMalloc(&sl.arena, need));
+            sl.arena_bytes = need;
+        }
+        uint8_t* dptr[16];
+        size_t pos = 0;
+        for (int a = 0; a < nargs; a++) {
+            dptr[a] = sl.arena + pos;
+            pos += ((args[a].bytes_per_lane * chunk + 255) & ~(size_t)255);
+            if (args[a].in)
+                CU(ctx, cudaMemcpyAsync(dptr[a], args[a].in + off * args[a].bytes_per_lane, m * args[a].bytes_per_lane,
+                                        cudaMemcpyHostToDevice, sl.stream));
+        }
+        rc = launch(m, dptr, sl);
+        if (rc) return rc;
+        for (int a = 0; a < nargs; a++)
+            if (args[a].out)
+                CU(ctx, cudaMemcpyAsync(args[a].out + off * args[a].bytes_per_lane, dptr[a], m * args[a].bytes_per_lane,
+                                        cudaMemcpyDeviceToHost, sl.stream));
+    }
+    return bjj_sync(ctx);
+}
+
+#define H_IN(p, b) HostArg{(p), nullptr, (b)}
+#define H_OUT(p, b) HostArg{nullptr, (p), (b)}
+#define CHECK_LAUNCH(ctx)            \
+    (ctx)->launches++;               \
+    CU(ctx, cudaGetLastError());     \
+    return BJJ_OK;
+
+extern "C" {
+
+int bjj_fr_op_batch(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (!ctx || !a || !out || op < 0 || op > 4) return BJJ_ERR_ARG;
+    if (!b) b = a;
+    HostArg args[] = {H_IN(a, 32), H_IN(b, 32), H_OUT(out, 32)};
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_fr_op<<<grid_for(ctx, (const void*)k_fr_op, m), BJJ_BLOCK, 0, sl.stream>>>(op, m, d[0], d[1], d[2], ctx->flags_dev);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_add_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz, const uint8_t* qx,
+                  const uint8_t* qy, const uint8_t* qz, uint8_t* rx, uint8_t* ry, uint8_t* rz) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(pz, 32), H_IN(qx, 32), H_IN(qy, 32),
+                      H_IN(qz, 32), H_OUT(rx, 32), H_OUT(ry, 32), H_OUT(rz, 32)};
+    return run_host(ctx, n, args, 9, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_add<<<grid_for(ctx, (const void*)k_add, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4], d[5], d[6],
+                                                                                d[7], d[8], ctx->flags_dev);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_affine_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz, uint8_t* rx,
+                     uint8_t* ry) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(pz, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_affine<<<grid_for(ctx, (const void*)k_affine, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4],
+                                                                                      ctx->flags_dev);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar32,
+                         uint8_t* rx, uint8_t* ry) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        return launch_mul_scalar(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.table, &sl.table_slots);
+    });
+}
+
+int bjj_fixed_base_batch(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], ctx->comb);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_public_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* rx, uint8_t* ry) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(key32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_public<<<grid_for(ctx, (const void*)k_public, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], ctx->comb);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_sign_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, uint8_t* r8y,
+                   uint8_t* s32, uint8_t* status) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(key32, 32), H_IN(msg32, 32), H_OUT(r8x, 32), H_OUT(r8y, 32), H_OUT(s32, 32), H_OUT(status, 1)};
+    return run_host(ctx, n, args, 6, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_sign<<<grid_for(ctx, (const void*)k_sign, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4], d[5], ctx->comb);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_scalar_key_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* scalar32) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(key32, 32), H_OUT(scalar32, 32)};
+    return run_host(ctx, n, args, 2, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_scalar_key<<<grid_for(ctx, (const void*)k_scalar_key, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1]);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_compress_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, uint8_t* out32) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_OUT(out32, 32)};
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_compress<<<grid_for(ctx, (const void*)k_compress, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], ctx->flags_dev);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_decompress_batch(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* rx, uint8_t* ry, uint8_t* status) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(in32, 32), H_OUT(rx, 32), H_OUT(ry, 32), H_OUT(status, 1)};
+    return run_host(ctx, n, args, 4, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        k_decompress<<<grid_for(ctx, (const void*)k_decompress, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3]);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_poseidon_batch(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out) {
+    if (!ctx || !in || n_inputs < 1 || n_inputs > 8) return BJJ_ERR_ARG;
+    HostArg args[9];
+    for (int j = 0; j < n_inputs; j++) args[j] = H_IN(in[j], 32);
+    args[n_inputs] = H_OUT(out, 32);
+    return run_host(ctx, n, args, n_inputs + 1, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        return launch_poseidon(ctx, n_inputs, m, (const uint8_t* const*)d, d[n_inputs], sl.stream);
+    });
+}
+
+int bjj_verify_batch(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32,
+                     const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(r8x, 32), H_IN(r8y, 32), H_IN(s32, 32), H_IN(ax, 32), H_IN(ay, 32), H_IN(msg32, 32), H_OUT(ok, 1)};
+    return run_host(ctx, n, args, 7, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.table, &sl.table_slots);
+    });
+}
+
+int bjj_verify_compressed_batch(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
+                                const uint8_t* msg32, uint8_t* ok, uint8_t* status) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(sig64, 64), H_IN(pk32, 32), H_IN(msg32, 32), H_OUT(ok, 1), H_OUT(status, 1)};
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        return launch_verify_compressed(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.table, &sl.table_slots);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// Fr: the BN254 scalar field (BabyJubJub base field), 8 x 32-bit limbs, Montgomery form, R = 2^256.
+//
+// Replaces the reference's `Fr` (src/lib.rs:7 = poseidon_rs::Fr, an ff_ce #[derive(PrimeField)]
+// 4x64-bit Montgomery field; Cargo.toml:12,20).  Field arithmetic is exact, so any correct mod-Q
+// implementation is bit-identical at the canonical-bytes boundary.
+//
+// Representation invariant ("lazy"): every Fr held in registers is in [0, 2Q).  Because 4Q < 2^256,
+//   * mont_mul of two values < 2Q returns a value < 2Q with NO final conditional subtraction,
+//   * a + b < 4Q never overflows 256 bits, one conditional subtraction of 2Q restores the range.
+// fr_reduce() produces the canonical value in [0, Q) before any comparison / store.
+//
+// The multiplier is built from 4-product carry chains: for a fixed b_i, the products a_j*b_i with j
+// even put lo at column i+j and hi at column i+j+1 -- 8 distinct consecutive columns, one carry
+// chain.  Products with j odd form a second chain shifted by one column.  Two accumulators X / Y
+// (absolute columns) receive the chains alternately, so no product ever needs a carry fix-up.
+// nvcc -arch=sm_100a fuses each mad.lo.cc / madc.hi.cc pair into ONE IMAD.WIDE.U32[.X]:
+// one Montgomery multiplication = 128 IMAD.WIDE + 8 IMAD (m_i) = 136 fma-pipe instructions.
+//
+// Everything is __host__ __device__: the host build (BJJ_HOST_EMU, used ONLY by the CPU test
+// harness tests/hostemu) swaps the PTX chains for a 64-bit C emulation so the limb schedules,
+// curve formulas, recodings and table logic can be validated against the oracle without a GPU.
+// The shipped library (libbjj_cuda.so) contains device code only and has no CPU fallback.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BJJ_HD __host__ __device__ __forceinline__
+#define BJJ_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define BJJ_HD inline
+#define BJJ_HD_NOINLINE
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define BJJ_DEVICE_CODE 1
+#else
+#define BJJ_DEVICE_CODE 0
+#endif
+
+#if defined(__CUDACC__) && !defined(BJJ_HOST_EMU)
+#define BJJ_CONST __constant__ const
+#define BJJ_TABLE __device__ const
+#else
+#define BJJ_CONST static const
+#define BJJ_TABLE static const
+#endif
+
+#include "generated/bjj_consts.inc"
+
+namespace bjj {
+
+struct Fr {
+    uint32_t v[8];
+};
+
+// ------------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ------------------------------------------------------------------------------------------------
+
+// c[0..7] += {a0,a1,a2,a3} * b  laid out lo->c[2k], hi->c[2k+1].
+// TOP = 0: the chain provably produces no carry-out;  1: carry-out added into c[8];
+//       2: carry-out rippled into c[8], c[9] (dot products, where c[8] already holds data).
+// SEED: the chain starts with carry-in = carry(sx + sy)  (column fold of the previous step).
+#define BJJ_MAC4_BODY(FIRST)                                                                        \
+    FIRST ".lo.cc.u32 %0, %10, %14, %0;\n\tmadc.hi.cc.u32 %1, %10, %14, %1;\n\t"                    \
+          "madc.lo.cc.u32 %2, %11, %14, %2;\n\tmadc.hi.cc.u32 %3, %11, %14, %3;\n\t"                \
+          "madc.lo.cc.u32 %4, %12, %14, %4;\n\tmadc.hi.cc.u32 %5, %12, %14, %5;\n\t"                \
+          "madc.lo.cc.u32 %6, %13, %14, %6;\n\tmadc.hi.cc.u32 %7, %13, %14, %7;\n\t"                \
+          "addc.cc.u32 %8, %8, 0;\n\taddc.u32 %9, %9, 0;\n\t"
+#define BJJ_MAC4_OPERANDS                                                                           \
+    : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), \
+      "+r"(t8), "+r"(t9)                                                                            \
+    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b), "r"(sx), "r"(sy)
+
+template <bool SEED, int TOP>
+BJJ_HD void mac4(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b,
+                 uint32_t sx = 0, uint32_t sy = 0) {
+#if BJJ_DEVICE_CODE
+    // Unused tops are fed as dead zero temporaries; ptxas drops the dead addc instructions.
+    uint32_t t8 = (TOP >= 1) ? c[8] : 0u, t9 = (TOP >= 2) ? c[9] : 0u;
+    if (SEED) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %15, %16;\n\t" BJJ_MAC4_BODY("madc") "}" BJJ_MAC4_OPERANDS);
+    } else {
+        asm(BJJ_MAC4_BODY("mad") BJJ_MAC4_OPERANDS);
+    }
+    if (TOP >= 1) c[8] = t8;
+    if (TOP >= 2) c[9] = t9;
+#else
+    uint64_t carry = SEED ? (((uint64_t)sx + sy) >> 32) : 0;
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)a[k] * b;
+        uint64_t t = (uint64_t)c[2 * k] + (uint32_t)p + carry;
+        c[2 * k] = (uint32_t)t;
+        carry = t >> 32;
+        t = (uint64_t)c[2 * k + 1] + (p >> 32) + carry;
+        c[2 * k + 1] = (uint32_t)t;
+        carry = t >> 32;
+    }
+    if (TOP >= 1) {
+        uint64_t t = (uint64_t)c[8] + carry;
+        c[8] = (uint32_t)t;
+        carry = t >> 32;
+        if (TOP >= 2) c[9] += (uint32_t)carry;
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// add / sub / reduce
+// ------------------------------------------------------------------------------------------------
+
+// r = a + b (plain 256-bit, no reduction); returns carry-out
+BJJ_HD uint32_t add256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if BJJ_DEVICE_CODE
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\taddc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\taddc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+#endif
+}
+
+// r = a - b (plain 256-bit); returns 0 or 0xffffffff (borrow mask)
+BJJ_HD uint32_t sub256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if BJJ_DEVICE_CODE
+    uint32_t m;
+    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\tsubc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\tsubc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(m)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return m;
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (int64_t)a[i] - (int64_t)b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;   // 0 or 0xffffffff
+#endif
+}
+
+#define BJJ_LIMBS8(P) {P##0, P##1, P##2, P##3, P##4, P##5, P##6, P##7}
+
+// a in [0, 4Q)  ->  [0, 2Q)
+BJJ_HD void fr_cond_sub_2q(Fr& a) {
+    const uint32_t twoq[8] = BJJ_LIMBS8(BJJ_2Q);
+    uint32_t t[8];
+    uint32_t borrow = sub256(t, a.v, twoq);
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+// r = a + b  (lazy domain)
+BJJ_HD void fr_add(Fr& r, const Fr& a, const Fr& b) {
+    add256(r.v, a.v, b.v);
+    fr_cond_sub_2q(r);
+}
+
+// r = a - b  (lazy domain)
+BJJ_HD void fr_sub(Fr& r, const Fr& a, const Fr& b) {
+    const uint32_t twoq[8] = BJJ_LIMBS8(BJJ_2Q);
+    uint32_t t[8], m[8];
+    uint32_t borrow = sub256(t, a.v, b.v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = twoq[i] & borrow;
+    add256(r.v, t, m);
+}
+
+BJJ_HD void fr_dbl(Fr& r, const Fr& a) { fr_add(r, a, a); }
+
+BJJ_HD void fr_zero(Fr& r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+
+BJJ_HD void fr_neg(Fr& r, const Fr& a) {
+    Fr z;
+    fr_zero(z);
+    fr_sub(r, z, a);
+}
+
+// canonical value in [0, Q)
+BJJ_HD void fr_reduce(Fr& a) {
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    uint32_t t[8];
+    uint32_t borrow = sub256(t, a.v, q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+// plain 256-bit comparisons on canonical / raw integers
+BJJ_HD bool u256_eq(const uint32_t* a, const uint32_t* b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
+    return d == 0;
+}
+BJJ_HD bool u256_is_zero(const uint32_t* a) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a[i];
+    return d == 0;
+}
+// a < b
+BJJ_HD bool u256_lt(const uint32_t* a, const uint32_t* b) {
+    uint32_t t[8];
+    return sub256(t, a, b) != 0;
+}
+
+// value == 0 mod Q, for a in the lazy domain [0, 2Q)
+BJJ_HD bool fr_is_zero(const Fr& a) {
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    return u256_is_zero(a.v) || u256_eq(a.v, q);
+}
+
+// a == b mod Q (lazy inputs)
+BJJ_HD bool fr_eq(const Fr& a, const Fr& b) {
+    Fr x = a, y = b;
+    fr_reduce(x);
+    fr_reduce(y);
+    return u256_eq(x.v, y.v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery multiplication
+// ------------------------------------------------------------------------------------------------
+
+// One interleaved CIOS step at absolute column I.  S is the accumulator whose chain starts at column
+// I (X when I is even, Y when I is odd), N the other one.  FOLD: carry of column I-1 enters the chain.
+//
+// Column bound: after step I the running total is < 2^(32(I+1)) * (a + Q) < 2^(32(I+9)) because
+// a + Q < 3Q < 2^256, and X, Y are each <= the total.  Hence the N chain (columns I+1..I+8) never
+// carries out (TOP = 0) and the S chain (columns I..I+7) carries into a fresh S[I+8] (TOP = 1).
+#define BJJ_MUL_STEP(S, N, I, FOLD)                                                                   \
+    {                                                                                                   \
+        mac4<FOLD, 1>(&S[I], a.v[0], a.v[2], a.v[4], a.v[6], b.v[I], X[(I) ? (I)-1 : 0], Y[(I) ? (I)-1 : 0]); \
+        mac4<false, 0>(&N[I + 1], a.v[1], a.v[3], a.v[5], a.v[7], b.v[I]);                              \
+        uint32_t m = (S[I] + N[I]) * BJJ_NINV32;                                                        \
+        mac4<false, 1>(&S[I], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);                                       \
+        mac4<false, 0>(&N[I + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);                                   \
+    }
+
+// result limbs = columns 8..15 of X + Y, plus the carry of column 7 (X[7] + Y[7] is 0 or 2^32)
+BJJ_HD void fr_merge_xy(Fr& r, const uint32_t* X, const uint32_t* Y) {
+#if BJJ_DEVICE_CODE
+    asm("{\n\t.reg .u32 t;\n\t"
+        "add.cc.u32 t, %8, %9;\n\t"
+        "addc.cc.u32 %0, %10, %18;\n\taddc.cc.u32 %1, %11, %19;\n\taddc.cc.u32 %2, %12, %20;\n\t"
+        "addc.cc.u32 %3, %13, %21;\n\taddc.cc.u32 %4, %14, %22;\n\taddc.cc.u32 %5, %15, %23;\n\t"
+        "addc.cc.u32 %6, %16, %24;\n\taddc.u32 %7, %17, %25;\n\t}"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(X[7]), "r"(Y[7]),
+          "r"(X[8]), "r"(X[9]), "r"(X[10]), "r"(X[11]), "r"(X[12]), "r"(X[13]), "r"(X[14]), "r"(X[15]),
+          "r"(Y[8]), "r"(Y[9]), "r"(Y[10]), "r"(Y[11]), "r"(Y[12]), "r"(Y[13]), "r"(Y[14]), "r"(Y[15]));
+#else
+    uint64_t c = ((uint64_t)X[7] + Y[7]) >> 32;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)X[8 + i] + Y[8 + i];
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#endif
+}
+
+// r = a * b / 2^256 mod Q;  a, b in [0, 2Q)  ->  r in [0, 2Q)   (also valid for a < 2^256, b < Q)
+BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) {
+    uint32_t X[18], Y[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) X[i] = Y[i] = 0;
+    BJJ_MUL_STEP(X, Y, 0, false)
+    BJJ_MUL_STEP(Y, X, 1, true)
+    BJJ_MUL_STEP(X, Y, 2, true)
+    BJJ_MUL_STEP(Y, X, 3, true)
+    BJJ_MUL_STEP(X, Y, 4, true)
+    BJJ_MUL_STEP(Y, X, 5, true)
+    BJJ_MUL_STEP(X, Y, 6, true)
+    BJJ_MUL_STEP(Y, X, 7, true)
+    fr_merge_xy(r, X, Y);
+}
+
+// One step of a Montgomery dot product  sum_p A_p * B_p  at column I (see fr_dot).
+#define BJJ_DOT_STEP(S, N, I, FOLD)                                                                   \
+    {                                                                                                   \
+        _Pragma("unroll") for (int p = 0; p < NP; p++) {                                                \
+            if (FOLD && p == 0)                                                                         \
+                mac4<true, 2>(&S[I], A[p].v[0], A[p].v[2], A[p].v[4], A[p].v[6], B[p].v[I], X[(I) ? (I)-1 : 0], Y[(I) ? (I)-1 : 0]); \
+            else                                                                                        \
+                mac4<false, 2>(&S[I], A[p].v[0], A[p].v[2], A[p].v[4], A[p].v[6], B[p].v[I]);           \
+            mac4<false, 1>(&N[I + 1], A[p].v[1], A[p].v[3], A[p].v[5], A[p].v[7], B[p].v[I]);           \
+        }                                                                                               \
+        uint32_t m = (S[I] + N[I]) * BJJ_NINV32;                                                        \
+        mac4<false, 2>(&S[I], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);                                       \
+        mac4<false, 1>(&N[I + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);                                   \
+    }
+
+// r = (sum_{p<NP} A_p * B_p) / 2^256 mod Q  with ONE interleaved reduction (NP*64 + 72 IMADs instead
+// of NP*136).  Requirements: every A_p canonical (< Q), every B_p in the lazy domain (< 2Q),
+// NP <= 9.  Column bound: total after step I < 2^(32(I+1)) * (NP*Q + Q) < 2^(32(I+9)+2), so the
+// tops ripple one limb further than in fr_mul.  The result is < (2*NP*Q/2^256 + 1) * Q <= 4.4Q
+// < 2^256 and is brought back to [0, 2Q) by one (NP <= 7) or two conditional subtractions.
+template <int NP>
+BJJ_HD void fr_dot(Fr& r, const Fr* A, const Fr* B) {
+    uint32_t X[19], Y[19];
+#pragma unroll
+    for (int i = 0; i < 19; i++) X[i] = Y[i] = 0;
+    BJJ_DOT_STEP(X, Y, 0, false)
+    BJJ_DOT_STEP(Y, X, 1, true)
+    BJJ_DOT_STEP(X, Y, 2, true)
+    BJJ_DOT_STEP(Y, X, 3, true)
+    BJJ_DOT_STEP(X, Y, 4, true)
+    BJJ_DOT_STEP(Y, X, 5, true)
+    BJJ_DOT_STEP(X, Y, 6, true)
+    BJJ_DOT_STEP(Y, X, 7, true)
+    fr_merge_xy(r, X, Y);
+    fr_cond_sub_2q(r);
+    if (NP > 7) fr_cond_sub_2q(r);
+}
+
+BJJ_HD void fr_sqr(Fr& r, const Fr& a) { fr_mul(r, a, a); }
+
+// ------------------------------------------------------------------------------------------------
+// conversions and helpers
+// ------------------------------------------------------------------------------------------------
+
+BJJ_HD void fr_set(Fr& r, const uint32_t* w) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = w[i];
+}
+
+BJJ_HD Fr fr_const(const uint32_t* w) {
+    Fr r;
+    fr_set(r, w);
+    return r;
+}
+
+// any 256-bit integer -> Montgomery form of (x mod Q), lazy domain.  R2 must be the FIRST operand:
+// the column bound of fr_mul needs a + Q < 2^256 for the multiplicand `a`, while `b` may be any
+// 256-bit value as long as a*b < Q*2^256.
+BJJ_HD void fr_to_mont(Fr& r, const Fr& x) {
+    Fr r2 = fr_const(BJJ_R2);
+    fr_mul(r, r2, x);
+}
+
+// Montgomery form -> canonical integer in [0, Q)
+BJJ_HD void fr_from_mont(Fr& r, const Fr& a) {
+    Fr one;
+    fr_zero(one);
+    one.v[0] = 1;
+    fr_mul(r, a, one);
+    fr_reduce(r);
+}
+
+BJJ_HD void fr_cmov(Fr& r, const Fr& a, bool take) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = take ? a.v[i] : r.v[i];
+}
+
+// r = a^e for a public 256-bit exponent (plain binary, MSB first).  Not unrolled: one sqr + one mul
+// body in the instruction stream.
+BJJ_HD void fr_pow(Fr& r, const Fr& a, const uint32_t* e, int nbits) {
+    Fr acc = fr_const(BJJ_ONE_M);
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        fr_sqr(acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) fr_mul(acc, acc, a);
+    }
+    r = acc;
+}
+
+// Fermat inverse; 0 -> 0.
+BJJ_HD void fr_inv(Fr& r, const Fr& a) { fr_pow(r, a, BJJ_EXP_QM2, 254); }
+
+}  // namespace bjj

@@ -1,0 +1,732 @@
+// Per-lane bodies of the batch kernels.  One lane = one element of the SoA batch.
+//
+// Boundary layout (include/bjj_cuda.h): every field element / scalar / compressed point is 32 bytes
+// little-endian at byte offset 32*i of its own array (SoA), i.e. 8 x u32 = two 16-byte vector loads
+// per lane, 1 KiB contiguous per warp.
+//
+// Each lane function cites the reference item it replaces (paths into /root/reference).
+#pragma once
+#include <string.h>
+#include "blake512.cuh"
+#include "curve.cuh"
+#include "fr.cuh"
+#include "poseidon.cuh"
+
+namespace bjj {
+
+struct alignas(16) U128 {
+    uint32_t x, y, z, w;
+};
+
+// ---- lane I/O -------------------------------------------------------------------------------------
+BJJ_HD void load_u256(uint32_t* w, const uint8_t* base, size_t i) {
+#if BJJ_DEVICE_CODE
+    const uint4* p = reinterpret_cast<const uint4*>(base + 32 * i);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    memcpy(w, base + 32 * i, 32);
+#endif
+}
+BJJ_HD void store_u256(uint8_t* base, size_t i, const uint32_t* w) {
+#if BJJ_DEVICE_CODE
+    uint4* p = reinterpret_cast<uint4*>(base + 32 * i);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+#else
+    memcpy(base + 32 * i, w, 32);
+#endif
+}
+
+// status / error bits -------------------------------------------------------------------------------
+// per-lane status byte of decompress (maps 1:1 to the reference's error strings)
+#define BJJ_ST_OK 0
+#define BJJ_ST_Y_RANGE 1      // "y outside the Finite Field over R"   src/lib.rs:202
+#define BJJ_ST_NO_INV 2       // "no mod inv of Zero"                  src/utils.rs:14
+#define BJJ_ST_NOT_SQUARE 3   // "not a mod p square"                  src/utils.rs:119
+// batch-level flag bits (device word OR-ed by lanes)
+#define BJJ_FLAG_NONCANONICAL 1u   // a field-element input was >= Q (cannot happen through the Rust types)
+
+// canonical bytes -> Montgomery; *flags |= NONCANONICAL if the integer is >= Q (value is reduced)
+BJJ_HD void load_fr(Fr& r, const uint8_t* base, size_t i, uint32_t& flags) {
+    Fr raw;
+    load_u256(raw.v, base, i);
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (!u256_lt(raw.v, q)) flags |= BJJ_FLAG_NONCANONICAL;
+    fr_to_mont(r, raw);
+}
+BJJ_HD void store_fr(uint8_t* base, size_t i, const Fr& a) {
+    Fr c;
+    fr_from_mont(c, a);
+    store_u256(base, i, c.v);
+}
+
+// ---- per-thread window table in global memory --------------------------------------------------------
+// 9 Niels entries (0 = identity, j = j*P) x 8 x 16 B, interleaved across threads:
+//   U128 index = (entry*8 + q) * stride + slot       (q = coordinate*2 + half)
+struct LaneTable {
+    U128* base;
+    size_t stride;
+    size_t slot;
+};
+#define BJJ_TABLE_ENTRIES 9
+#define BJJ_TABLE_U128_PER_LANE (BJJ_TABLE_ENTRIES * 8)
+
+BJJ_HD void table_store(const LaneTable& t, int e, const Niels& n) {
+    const Fr* f[4] = {&n.ypx, &n.ymx, &n.t2d, &n.z2};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            U128 u;
+            u.x = f[c]->v[4 * h + 0];
+            u.y = f[c]->v[4 * h + 1];
+            u.z = f[c]->v[4 * h + 2];
+            u.w = f[c]->v[4 * h + 3];
+            t.base[(size_t)(e * 8 + c * 2 + h) * t.stride + t.slot] = u;
+        }
+    }
+}
+BJJ_HD void table_load(Niels& n, const LaneTable& t, int e) {
+    Fr* f[4] = {&n.ypx, &n.ymx, &n.t2d, &n.z2};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            U128 u = t.base[(size_t)(e * 8 + c * 2 + h) * t.stride + t.slot];
+            f[c]->v[4 * h + 0] = u.x;
+            f[c]->v[4 * h + 1] = u.y;
+            f[c]->v[4 * h + 2] = u.z;
+            f[c]->v[4 * h + 3] = u.w;
+        }
+    }
+}
+
+// entries 0..8 = j*P
+BJJ_HD void table_build(const LaneTable& t, const PointExt& p) {
+    Niels n, n1;
+    niels_identity(n);
+    table_store(t, 0, n);
+    niels_from_ext(n1, p);
+    table_store(t, 1, n1);
+    PointExt acc;
+    ext_dbl<true>(acc, p);
+    niels_from_ext(n, acc);
+    table_store(t, 2, n);
+#pragma unroll 1
+    for (int j = 3; j <= 8; j++) {
+        ext_add_niels<true>(acc, acc, n1);
+        niels_from_ext(n, acc);
+        table_store(t, j, n);
+    }
+}
+
+// signed digit d in [-8, 8] -> Niels of d*P
+BJJ_HD void table_select(Niels& n, const LaneTable& t, int d) {
+    int ad = d < 0 ? -d : d;
+    table_load(n, t, ad);
+    niels_cneg(n, d < 0);
+}
+
+// ---- fixed-base comb for B8 ------------------------------------------------------------------------
+// comb[w][j] = j * 256^w * B8 as affine Niels (y+x, y-x, 2d'xy) on the a = -1 model, j = 0..128,
+// w = 0..32 (w = 32 only holds j = 0, 1 for the recoding carry).  Built once per context on the device.
+#define BJJ_COMB_WINDOWS 33
+#define BJJ_COMB_ENTRIES 129
+struct CombEntry {   // 96 bytes
+    uint32_t ypx[8], ymx[8], t2d[8];
+};
+
+BJJ_HD void comb_select(NielsAff& n, const CombEntry* comb, int w, int d) {
+    int ad = d < 0 ? -d : d;
+    const CombEntry* e = comb + (size_t)w * BJJ_COMB_ENTRIES + ad;
+#if BJJ_DEVICE_CODE
+    const uint4* p = reinterpret_cast<const uint4*>(e);
+    uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4), q5 = __ldg(p + 5);
+    n.ypx.v[0] = q0.x; n.ypx.v[1] = q0.y; n.ypx.v[2] = q0.z; n.ypx.v[3] = q0.w;
+    n.ypx.v[4] = q1.x; n.ypx.v[5] = q1.y; n.ypx.v[6] = q1.z; n.ypx.v[7] = q1.w;
+    n.ymx.v[0] = q2.x; n.ymx.v[1] = q2.y; n.ymx.v[2] = q2.z; n.ymx.v[3] = q2.w;
+    n.ymx.v[4] = q3.x; n.ymx.v[5] = q3.y; n.ymx.v[6] = q3.z; n.ymx.v[7] = q3.w;
+    n.t2d.v[0] = q4.x; n.t2d.v[1] = q4.y; n.t2d.v[2] = q4.z; n.t2d.v[3] = q4.w;
+    n.t2d.v[4] = q5.x; n.t2d.v[5] = q5.y; n.t2d.v[6] = q5.z; n.t2d.v[7] = q5.w;
+#else
+    fr_set(n.ypx, e->ypx);
+    fr_set(n.ymx, e->ymx);
+    fr_set(n.t2d, e->t2d);
+#endif
+    niels_aff_cneg(n, d < 0);
+}
+
+// acc = k * B8 for a 256-bit k: 33 mixed additions, no doublings.
+BJJ_HD void fixed_base_comb(PointExt& acc, const CombEntry* comb, const uint32_t* k) {
+    Recode8 rc;
+    recode8(rc, k);
+    ext_identity(acc);
+    NielsAff n;
+    comb_select(n, comb, 32, (int)rc.top);
+    ext_add_niels_aff<true>(acc, acc, n);
+#pragma unroll 1
+    for (int w = 31; w >= 0; w--) {
+        comb_select(n, comb, w, recode8_digit(rc, w));
+        ext_add_niels_aff<true>(acc, acc, n);
+    }
+}
+
+// one comb entry: j * 256^w * B8   (init kernel; one thread per (w, j))
+BJJ_HD void comb_build_entry(CombEntry* comb, int w, int j) {
+    CombEntry* e = comb + (size_t)w * BJJ_COMB_ENTRIES + j;
+    PointAff b8;
+    b8.x = fr_const(BJJ_B8X_M);
+    b8.y = fr_const(BJJ_B8Y_M);
+    PointExt base, acc;
+    ext_from_affine(base, b8);
+#pragma unroll 1
+    for (int i = 0; i < 8 * w; i++) ext_dbl<true>(base, base);
+    ext_identity(acc);
+    Niels nb;
+    niels_from_ext(nb, base);
+#pragma unroll 1
+    for (int bit = 7; bit >= 0; bit--) {
+        ext_dbl<true>(acc, acc);
+        if ((j >> bit) & 1) ext_add_niels<true>(acc, acc, nb);
+    }
+    // affine on the a = -1 model, then Niels form
+    Fr zi, x, y, t;
+    fr_inv(zi, acc.Z);
+    fr_mul(x, acc.X, zi);
+    fr_mul(y, acc.Y, zi);
+    fr_mul(t, x, y);
+    const Fr d2 = fr_const(BJJ_TWO_DP_M);
+    fr_mul(t, t, d2);
+    Fr ypx, ymx;
+    fr_add(ypx, y, x);
+    fr_sub(ymx, y, x);
+    fr_reduce(ypx);
+    fr_reduce(ymx);
+    fr_reduce(t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        e->ypx[i] = ypx.v[i];
+        e->ymx[i] = ymx.v[i];
+        e->t2d[i] = t.v[i];
+    }
+}
+
+// ---- affine output ------------------------------------------------------------------------------------
+// a = -1 extended -> canonical affine bytes on the original curve (Fermat inverse per lane)
+BJJ_HD void store_ext_affine(uint8_t* rx, uint8_t* ry, size_t i, const PointExt& p) {
+    PointProj pj;
+    ext_to_proj(pj, p);
+    PointAff a;
+    proj_affine(a, pj);
+    store_fr(rx, i, a.x);
+    store_fr(ry, i, a.y);
+}
+
+// ---- lane bodies --------------------------------------------------------------------------------------
+
+// test hook for Fr (reference Fr ops: mul_assign / square / add_assign / sub_assign / inverse)
+#define BJJ_FR_OP_MUL 0
+#define BJJ_FR_OP_ADD 1
+#define BJJ_FR_OP_SUB 2
+#define BJJ_FR_OP_INV 3
+#define BJJ_FR_OP_SQR 4
+BJJ_HD void lane_fr_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t i, uint32_t& flags) {
+    Fr x, y, r;
+    load_fr(x, a, i, flags);
+    load_fr(y, b, i, flags);
+    switch (op) {
+        case BJJ_FR_OP_MUL: fr_mul(r, x, y); break;
+        case BJJ_FR_OP_ADD: fr_add(r, x, y); break;
+        case BJJ_FR_OP_SUB: fr_sub(r, x, y); break;
+        case BJJ_FR_OP_INV: fr_inv(r, x); break;
+        default: fr_sqr(r, x); break;
+    }
+    store_fr(out, i, r);
+}
+
+// PointProjective::add (src/lib.rs:88-131), projective in, projective out, literal formula
+BJJ_HD void lane_add(const uint8_t* px, const uint8_t* py, const uint8_t* pz, const uint8_t* qx,
+                     const uint8_t* qy, const uint8_t* qz, uint8_t* rx, uint8_t* ry, uint8_t* rz, size_t i,
+                     uint32_t& flags) {
+    PointProj p, q, r;
+    load_fr(p.x, px, i, flags);
+    load_fr(p.y, py, i, flags);
+    load_fr(p.z, pz, i, flags);
+    load_fr(q.x, qx, i, flags);
+    load_fr(q.y, qy, i, flags);
+    load_fr(q.z, qz, i, flags);
+    proj_add_bbjlp(r, p, q);
+    store_fr(rx, i, r.x);
+    store_fr(ry, i, r.y);
+    store_fr(rz, i, r.z);
+}
+
+// PointProjective::affine (src/lib.rs:70-85)
+BJJ_HD void lane_affine(const uint8_t* px, const uint8_t* py, const uint8_t* pz, uint8_t* rx, uint8_t* ry,
+                        size_t i, uint32_t& flags) {
+    PointProj p;
+    load_fr(p.x, px, i, flags);
+    load_fr(p.y, py, i, flags);
+    load_fr(p.z, pz, i, flags);
+    PointAff a;
+    proj_affine(a, p);
+    store_fr(rx, i, a.x);
+    store_fr(ry, i, a.y);
+}
+
+// windowed variable-base ladder on the a = -1 model: acc = n * p  (p on the curve, n any 256-bit integer)
+BJJ_HD void var_base_mul(PointExt& acc, const PointExt& p, const uint32_t* n, const LaneTable& tbl) {
+    table_build(tbl, p);
+    Recode4 rc;
+    recode4(rc, n);
+    Niels nn;
+    ext_identity(acc);
+    table_select(nn, tbl, (int)rc.top);
+    ext_add_niels<false>(acc, acc, nn);
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        ext_dbl<false>(acc, acc);
+        ext_dbl<false>(acc, acc);
+        ext_dbl<false>(acc, acc);
+        ext_dbl<true>(acc, acc);
+        table_select(nn, tbl, recode4_digit(rc, i));
+        ext_add_niels<false>(acc, acc, nn);
+    }
+}
+
+BJJ_HD int clz32(uint32_t x) {
+#if BJJ_DEVICE_CODE
+    return __clz((int)x);
+#else
+    return __builtin_clz(x);
+#endif
+}
+
+// exact lane: the reference sequence, bit for bit (off-curve inputs).  Point::mul_scalar,
+// src/lib.rs:149-164: r = (0,1,1); exp = P; for bit i of n, LSB first, up to bits(n): if set
+// r = r.add(exp); exp = exp.add(exp);  then r.affine().
+BJJ_HD_NOINLINE void mul_scalar_exact(PointAff& r, const PointAff& p, const uint32_t* n, int nwords) {
+    PointProj acc, e;
+    fr_zero(acc.x);
+    acc.y = fr_const(BJJ_ONE_M);
+    acc.z = fr_const(BJJ_ONE_M);
+    e.x = p.x;
+    e.y = p.y;
+    e.z = fr_const(BJJ_ONE_M);
+    int nb = 0;     // BigInt::bits()
+    for (int i = 0; i < nwords; i++)
+        if (n[i]) nb = 32 * i + (32 - clz32(n[i]));
+#pragma unroll 1
+    for (int i = 0; i < nb; i++) {
+        if ((n[i >> 5] >> (i & 31)) & 1) proj_add_bbjlp(acc, acc, e);
+        proj_add_bbjlp(e, e, e);
+    }
+    proj_affine(r, acc);
+}
+
+// Point::mul_scalar (src/lib.rs:149-164): on-curve gate -> fast ladder, else exact lane.
+BJJ_HD void lane_mul_scalar(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, uint8_t* rx,
+                            uint8_t* ry, size_t i, const LaneTable& tbl, uint32_t& flags) {
+    PointAff p;
+    load_fr(p.x, px, i, flags);
+    load_fr(p.y, py, i, flags);
+    uint32_t n[8];
+    load_u256(n, scalar, i);
+    if (on_curve(p)) {
+        PointExt e, acc;
+        ext_from_affine(e, p);
+        var_base_mul(acc, e, n, tbl);
+        store_ext_affine(rx, ry, i, acc);
+    } else {
+        PointAff r;
+        mul_scalar_exact(r, p, n, 8);
+        store_fr(rx, i, r.x);
+        store_fr(ry, i, r.y);
+    }
+}
+
+// B8.mul_scalar(k) for a raw 256-bit scalar (src/lib.rs:305, :329, :405)
+BJJ_HD void lane_fixed_base(const uint8_t* scalar, uint8_t* rx, uint8_t* ry, size_t i, const CombEntry* comb) {
+    uint32_t k[8];
+    load_u256(k, scalar, i);
+    PointExt acc;
+    fixed_base_comb(acc, comb, k);
+    store_ext_affine(rx, ry, i, acc);
+}
+
+// PrivateKey::public (src/lib.rs:304-306) = B8 * scalar_key(key)
+BJJ_HD void lane_public(const uint8_t* key, uint8_t* rx, uint8_t* ry, size_t i, const CombEntry* comb) {
+    uint32_t kw[8], k[8];
+    load_u256(kw, key, i);
+    scalar_key_from_key(k, kw);
+    PointExt acc;
+    fixed_base_comb(acc, comb, k);
+    store_ext_affine(rx, ry, i, acc);
+}
+
+// PrivateKey::scalar_key (src/lib.rs:284-302) test hook
+BJJ_HD void lane_scalar_key(const uint8_t* key, uint8_t* out, size_t i) {
+    uint32_t kw[8], k[8];
+    load_u256(kw, key, i);
+    scalar_key_from_key(k, kw);
+    store_u256(out, i, k);
+}
+
+// Point::compress (src/lib.rs:166-178)
+BJJ_HD void lane_compress(const uint8_t* px, const uint8_t* py, uint8_t* out, size_t i, uint32_t& flags) {
+    uint32_t x[8], y[8];
+    load_u256(x, px, i);
+    load_u256(y, py, i);
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (!u256_lt(x, q) || !u256_lt(y, q)) flags |= BJJ_FLAG_NONCANONICAL;
+    if (u256_lt(BJJ_QHALF, x)) y[7] |= 0x80000000u;
+    store_u256(out, i, y);
+}
+
+// a^((T-1)/2) driven by the public exponent bits
+BJJ_HD uint32_t ph_lookup(const Fr& t) {
+    Fr c = t;
+    fr_reduce(c);
+    return BJJ_PH_LUT[(c.v[0] * BJJ_PH_HASH_MULT) >> 23];
+}
+
+// decompress_point (src/lib.rs:192-224) with utils::modinv / modsqrt (src/utils.rs:11-29, 109-160).
+// The reference's Tonelli-Shanks loop is replaced by a fixed schedule: x0 = a^((T+1)/2), b = a^T lies in
+// the order-2^28 subgroup; its discrete log k is found 7 bits at a time (Pohlig-Hellman with table
+// look-ups) and x = x0 * g^(-k/2).  The returned x does not depend on which root a sqrt algorithm finds
+// (src/lib.rs:217-220 fixes the sign), so the result is bit-identical.
+BJJ_HD uint32_t decompress_core(Fr& xm, Fr& ym, const uint32_t* bytes) {
+    uint32_t yw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) yw[i] = bytes[i];
+    const bool sign = (yw[7] >> 31) != 0;
+    yw[7] &= 0x7FFFFFFFu;
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (!u256_lt(yw, q)) return BJJ_ST_Y_RANGE;
+    Fr yraw;
+    fr_set(yraw, yw);
+    fr_to_mont(ym, yraw);
+    const Fr one = fr_const(BJJ_ONE_M), cA = fr_const(BJJ_A_M), cD = fr_const(BJJ_D_M);
+    Fr y2, u, v, vi, a;
+    fr_sqr(y2, ym);
+    fr_sub(u, one, y2);
+    fr_mul(v, cD, y2);
+    fr_sub(v, cA, v);
+    if (fr_is_zero(v)) return BJJ_ST_NO_INV;
+    fr_inv(vi, v);
+    fr_mul(a, u, vi);
+    if (fr_is_zero(a)) return BJJ_ST_NOT_SQUARE;     // modsqrt rejects a == 0 (src/utils.rs:118)
+    Fr w, x0, b, t;
+    fr_pow(w, a, BJJ_EXP_TM1H, BJJ_EXP_TM1H_BITS);
+    fr_mul(x0, a, w);
+    fr_mul(b, x0, w);
+    uint32_t k[4];
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        t = b;
+#pragma unroll 1
+        for (int s = 0; s < 21 - 7 * j; s++) fr_sqr(t, t);
+        k[j] = ph_lookup(t);
+        if (k[j] > 127) return BJJ_ST_NOT_SQUARE;
+        if (j == 0 && (k[0] & 1)) return BJJ_ST_NOT_SQUARE;    // odd discrete log: non-residue
+        Fr c = fr_const(BJJ_PH_NEG[j][k[j]]);
+        fr_mul(b, b, c);
+        Fr hc = fr_const(BJJ_PH_HALF[j][k[j]]);
+        fr_mul(x0, x0, hc);
+    }
+    fr_sqr(t, x0);
+    if (!fr_eq(t, a)) return BJJ_ST_NOT_SQUARE;
+    // sign rule (src/lib.rs:217-220): negate iff (x > Q>>1) != sign
+    Fr xc;
+    fr_from_mont(xc, x0);
+    const bool big = u256_lt(BJJ_QHALF, xc.v);
+    if (big != sign) fr_neg(x0, x0);
+    xm = x0;
+    return BJJ_ST_OK;
+}
+
+BJJ_HD void lane_decompress(const uint8_t* in, uint8_t* rx, uint8_t* ry, uint8_t* status, size_t i) {
+    uint32_t b[8];
+    load_u256(b, in, i);
+    Fr x, y;
+    fr_zero(x);
+    fr_zero(y);
+    uint32_t st = decompress_core(x, y, b);
+    if (st != BJJ_ST_OK) {
+        fr_zero(x);
+        fr_zero(y);
+    }
+    store_fr(rx, i, x);
+    store_fr(ry, i, y);
+    status[i] = (uint8_t)st;
+}
+
+// POSEIDON.hash(inputs) for NIN = T-1 inputs (src/lib.rs:400-401 uses NIN = 5)
+template <int T>
+BJJ_HD void lane_poseidon(const uint8_t* const* in, uint8_t* out, size_t i, uint32_t& flags) {
+    Fr st[T];
+    fr_zero(st[0]);
+#pragma unroll
+    for (int j = 1; j < T; j++) load_fr(st[j], in[j - 1], i, flags);
+    poseidon_permute<T>(st);
+    store_fr(out, i, st[0]);
+}
+
+// x (nwords 32-bit limbs) mod SUBORDER by shift-and-subtract, MSB first.  Signer-side only (two
+// reductions per signature), so clarity wins over speed.
+BJJ_HD void mod_suborder(uint32_t* out, const uint32_t* x, int nwords) {
+    uint32_t acc[8], t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0;
+#pragma unroll 1
+    for (int bit = nwords * 32 - 1; bit >= 0; bit--) {
+        // acc < l < 2^251, so acc*2 + b fits
+#pragma unroll
+        for (int i = 7; i > 0; i--) acc[i] = (acc[i] << 1) | (acc[i - 1] >> 31);
+        acc[0] = (acc[0] << 1) | ((x[bit >> 5] >> (bit & 31)) & 1u);
+        uint32_t borrow = sub256(t, acc, BJJ_SUBORDER);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = borrow ? acc[i] : t[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = acc[i];
+}
+
+// PrivateKey::sign (src/lib.rs:308-342).  status: 0 ok, 4 = "msg outside the Finite Field" (:310).
+//   h = BLAKE512(key); r = BLAKE512(h[32..64] || msg_le32) mod SUBORDER; R8 = B8*r; A = public();
+//   hm = Poseidon(R8.x, R8.y, A.x, A.y, msg);  S = (r + hm * (scalar_key << 3)) mod SUBORDER
+#define BJJ_ST_MSG_RANGE 4
+BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, const uint32_t* msg,
+                          const CombEntry* comb, Fr& r8x_m, Fr& r8y_m) {
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (u256_lt(q, msg)) return BJJ_ST_MSG_RANGE;
+    uint64_t le[4], h[8], m2[8], h2[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) le[i] = (uint64_t)key[2 * i] | ((uint64_t)key[2 * i + 1] << 32);
+    blake512_short<4>(h, le);
+    uint32_t sk[8];
+    scalar_key_from_digest(sk, h);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        m2[i] = h[4 + i];                                                        // digest bytes 32..63
+        m2[4 + i] = bswap64((uint64_t)msg[2 * i] | ((uint64_t)msg[2 * i + 1] << 32));   // msg, 32 LE bytes
+    }
+    blake512_short_be<8>(h2, m2);
+    uint32_t rw[16], r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {          // the 64 digest bytes read as a little-endian integer
+        uint64_t l = bswap64(h2[i]);
+        rw[2 * i] = (uint32_t)l;
+        rw[2 * i + 1] = (uint32_t)(l >> 32);
+    }
+    mod_suborder(r, rw, 16);
+    fixed_base_comb(r8, comb, r);
+    PointExt a;
+    fixed_base_comb(a, comb, sk);
+    // affine coordinates of R8 and A on the original curve
+    PointProj pj;
+    PointAff r8a, aa;
+    ext_to_proj(pj, r8);
+    proj_affine(r8a, pj);
+    ext_to_proj(pj, a);
+    proj_affine(aa, pj);
+    Fr st[6], mraw;
+    fr_zero(st[0]);
+    st[1] = r8a.x;
+    st[2] = r8a.y;
+    st[3] = aa.x;
+    st[4] = aa.y;
+    fr_set(mraw, msg);
+    fr_to_mont(st[5], mraw);
+    poseidon_permute<6>(st);
+    Fr hm;
+    fr_from_mont(hm, st[0]);
+    // prod = hm * (sk << 3) + r   (8 x 9 limbs -> 17 limbs)
+    uint32_t sk8[9], prod[18];
+    sk8[0] = sk[0] << 3;
+#pragma unroll
+    for (int i = 1; i < 8; i++) sk8[i] = (sk[i] << 3) | (sk[i - 1] >> 29);
+    sk8[8] = sk[7] >> 29;
+#pragma unroll
+    for (int i = 0; i < 18; i++) prod[i] = 0;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            c += (uint64_t)hm.v[i] * sk8[j] + prod[i + j];
+            prod[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        prod[i + 9] = (uint32_t)c;
+    }
+    uint64_t c = 0;
+#pragma unroll 1
+    for (int i = 0; i < 18; i++) {
+        c += (uint64_t)prod[i] + (i < 8 ? r[i] : 0u);
+        prod[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    mod_suborder(s_out, prod, 18);
+    r8x_m = r8a.x;
+    r8y_m = r8a.y;
+    return BJJ_ST_OK;
+}
+
+BJJ_HD void lane_sign(const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, uint8_t* r8y, uint8_t* s32,
+                      uint8_t* status, size_t i, const CombEntry* comb) {
+    uint32_t key[8], msg[8], s[8];
+    load_u256(key, key32, i);
+    load_u256(msg, msg32, i);
+    PointExt r8;
+    Fr x, y;
+    fr_zero(x);
+    fr_zero(y);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = 0;
+    uint32_t st = sign_core(r8, s, key, msg, comb, x, y);
+    store_fr(r8x, i, x);
+    store_fr(r8y, i, y);
+    store_u256(s32, i, s);
+    status[i] = (uint8_t)st;
+}
+
+// verify (src/lib.rs:395-412).  Returns 0/1 like the reference's bool.
+//   msg > Q -> false; hm = Poseidon(R8.x, R8.y, A.x, A.y, msg mod Q);
+//   accept iff  S*B8 == R8 + (8*hm)*A   compared in affine coordinates.
+// Fast lane (A and R8 on the curve): 8*hm*A = hm*(8A), so one Straus pass computes
+//   P = S*B8 + hm*(-8A)  and the test is  P == R8  checked projectively (no inversion).
+// Exact lane (any input point off the curve): the reference sequence replayed literally.
+BJJ_HD uint32_t verify_core(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m,
+                            const LaneTable& tbl, const CombEntry* comb) {
+    Fr st[6];
+    fr_zero(st[0]);
+    st[1] = r8.x;
+    st[2] = r8.y;
+    st[3] = a.x;
+    st[4] = a.y;
+    st[5] = msg_m;
+    poseidon_permute<6>(st);
+    Fr hm;
+    fr_from_mont(hm, st[0]);      // canonical integer hm < Q
+    if (on_curve(a) && on_curve(r8)) {
+        PointExt pa, acc;
+        ext_from_affine(pa, a);
+        ext_dbl<false>(pa, pa);
+        ext_dbl<false>(pa, pa);
+        ext_dbl<true>(pa, pa);
+        // negate: (-X, Y, Z, -T)
+        fr_neg(pa.X, pa.X);
+        fr_neg(pa.T, pa.T);
+        table_build(tbl, pa);
+        Recode4 ra;
+        recode4(ra, hm.v);
+        Recode8 rs;
+        recode8(rs, s);
+        ext_identity(acc);
+        Niels nn;
+        NielsAff nb;
+        table_select(nn, tbl, (int)ra.top);
+        ext_add_niels<true>(acc, acc, nn);
+        comb_select(nb, comb, 0, (int)rs.top);
+        ext_add_niels_aff<false>(acc, acc, nb);
+#pragma unroll 1
+        for (int i = 63; i >= 0; i--) {
+            ext_dbl<false>(acc, acc);
+            ext_dbl<false>(acc, acc);
+            ext_dbl<false>(acc, acc);
+            ext_dbl<true>(acc, acc);
+            table_select(nn, tbl, recode4_digit(ra, i));
+            if (i & 1) {
+                ext_add_niels<false>(acc, acc, nn);
+            } else {
+                ext_add_niels<true>(acc, acc, nn);
+                comb_select(nb, comb, 0, recode8_digit(rs, i >> 1));
+                ext_add_niels_aff<false>(acc, acc, nb);
+            }
+        }
+        // acc == R8 ?   X = x_R8 * sqrt(-a) * Z   and   Y = y_R8 * Z     (Z != 0: complete formulas)
+        const Fr sq = fr_const(BJJ_SQRT_NEG_A_M);
+        Fr lx, ly;
+        fr_mul(lx, r8.x, sq);
+        fr_mul(lx, lx, acc.Z);
+        fr_mul(ly, r8.y, acc.Z);
+        return (fr_eq(lx, acc.X) && fr_eq(ly, acc.Y)) ? 1u : 0u;
+    }
+    // exact lane
+    PointAff b8, l, ka, ra;
+    b8.x = fr_const(BJJ_B8X_M);
+    b8.y = fr_const(BJJ_B8Y_M);
+    mul_scalar_exact(l, b8, s, 8);
+    uint32_t k9[9];
+    k9[0] = hm.v[0] << 3;
+#pragma unroll
+    for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
+    k9[8] = hm.v[7] >> 29;
+    mul_scalar_exact(ka, a, k9, 9);
+    PointProj pr, pk, sum;
+    pr.x = r8.x;
+    pr.y = r8.y;
+    pr.z = fr_const(BJJ_ONE_M);
+    pk.x = ka.x;
+    pk.y = ka.y;
+    pk.z = fr_const(BJJ_ONE_M);
+    proj_add_bbjlp(sum, pr, pk);
+    proj_affine(ra, sum);
+    return (fr_eq(l.x, ra.x) && fr_eq(l.y, ra.y)) ? 1u : 0u;
+}
+
+BJJ_HD void lane_verify(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
+                        const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i, const LaneTable& tbl,
+                        const CombEntry* comb, uint32_t& flags) {
+    uint32_t msg[8], s[8];
+    load_u256(msg, msg32, i);
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (u256_lt(q, msg)) {     // msg > Q -> false; msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
+        ok[i] = 0;
+        return;
+    }
+    load_u256(s, s32, i);
+    PointAff r8, a;
+    load_fr(r8.x, r8x, i, flags);
+    load_fr(r8.y, r8y, i, flags);
+    load_fr(a.x, ax, i, flags);
+    load_fr(a.y, ay, i, flags);
+    Fr mraw, mm;
+    fr_set(mraw, msg);
+    fr_to_mont(mm, mraw);
+    ok[i] = (uint8_t)verify_core(r8, s, a, mm, tbl, comb);
+}
+
+// decompress_signature + decompress(pk) + verify (src/lib.rs:260-268, 192-224, 395-412):
+// sig64 = compress(R8) || S_le32, pk32 = compress(A).  status = first decompression error (R8 first,
+// then A), ok = 0 whenever status != 0.
+BJJ_HD void lane_verify_compressed(const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msg32, uint8_t* ok,
+                                   uint8_t* status, size_t i, const LaneTable& tbl, const CombEntry* comb) {
+    uint32_t rb[8], s[8], ab[8], msg[8];
+    load_u256(rb, sig64, 2 * i);
+    load_u256(s, sig64, 2 * i + 1);
+    load_u256(ab, pk32, i);
+    load_u256(msg, msg32, i);
+    PointAff r8, a;
+    uint32_t st = decompress_core(r8.x, r8.y, rb);
+    if (st == BJJ_ST_OK) st = decompress_core(a.x, a.y, ab);
+    status[i] = (uint8_t)st;
+    if (st != BJJ_ST_OK) {
+        ok[i] = 0;
+        return;
+    }
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (u256_lt(q, msg)) {
+        ok[i] = 0;
+        return;
+    }
+    Fr mraw, mm;
+    fr_set(mraw, msg);
+    fr_to_mont(mm, mraw);
+    ok[i] = (uint8_t)verify_core(r8, s, a, mm, tbl, comb);
+}
+
+}  // namespace bjj

@@ -1,0 +1,140 @@
+// TEST HARNESS ONLY -- never shipped, never loaded by the product.
+//
+// Compiles the device headers (babyjubjub-rs_b200/csrc/*.cuh) for the HOST with BJJ_HOST_EMU: the PTX
+// carry chains are replaced by their 64-bit C emulation, everything else (limb schedules, curve
+// formulas, recodings, table logic, Poseidon, square root) is the same source the GPU kernels
+// compile.  `pytest -m "not gpu"` uses it to validate that logic against the oracle in a container
+// without a GPU.  It is deliberately slow (one lane at a time, no threads).
+#define BJJ_HOST_EMU 1
+#include <stdlib.h>
+#include <vector>
+#include "../../babyjubjub-rs_b200/csrc/lanes.cuh"
+
+using namespace bjj;
+
+static CombEntry* g_comb = nullptr;
+static std::vector<U128> g_table(BJJ_TABLE_U128_PER_LANE);
+
+static LaneTable lane_table() {
+    LaneTable t;
+    t.base = g_table.data();
+    t.stride = 1;
+    t.slot = 0;
+    return t;
+}
+
+extern "C" {
+
+void emu_init() {
+    if (g_comb) return;
+    g_comb = (CombEntry*)calloc((size_t)BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES, sizeof(CombEntry));
+    for (int w = 0; w < BJJ_COMB_WINDOWS; w++)
+        for (int j = 0; j < BJJ_COMB_ENTRIES; j++) {
+            if (w == 32 && j > 1) continue;
+            comb_build_entry(g_comb, w, j);
+        }
+}
+
+uint32_t emu_fr_op(int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) lane_fr_op(op, a, b, out, i, flags);
+    return flags;
+}
+
+uint32_t emu_fr_dot6(size_t n, const uint8_t* a /*6 arrays concatenated*/, const uint8_t* b, uint8_t* out) {
+    // out_i = sum_p a_p[i] * b_p[i]   (exercises fr_dot<6>)
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) {
+        Fr A[6], B[6], r;
+        for (int p = 0; p < 6; p++) {
+            load_fr(A[p], a + 32 * n * p, i, flags);
+            fr_reduce(A[p]);
+            load_fr(B[p], b + 32 * n * p, i, flags);
+        }
+        fr_dot<6>(r, A, B);
+        store_fr(out, i, r);
+    }
+    return flags;
+}
+
+uint32_t emu_add(size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz, const uint8_t* qx,
+                 const uint8_t* qy, const uint8_t* qz, uint8_t* rx, uint8_t* ry, uint8_t* rz) {
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) lane_add(px, py, pz, qx, qy, qz, rx, ry, rz, i, flags);
+    return flags;
+}
+
+uint32_t emu_affine(size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz, uint8_t* rx, uint8_t* ry) {
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) lane_affine(px, py, pz, rx, ry, i, flags);
+    return flags;
+}
+
+uint32_t emu_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx, uint8_t* ry) {
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) lane_mul_scalar(px, py, k, rx, ry, i, lane_table(), flags);
+    return flags;
+}
+
+void emu_fixed_base(size_t n, const uint8_t* k, uint8_t* rx, uint8_t* ry) {
+    emu_init();
+    for (size_t i = 0; i < n; i++) lane_fixed_base(k, rx, ry, i, g_comb);
+}
+
+void emu_public(size_t n, const uint8_t* key, uint8_t* rx, uint8_t* ry) {
+    emu_init();
+    for (size_t i = 0; i < n; i++) lane_public(key, rx, ry, i, g_comb);
+}
+
+void emu_scalar_key(size_t n, const uint8_t* key, uint8_t* out) {
+    for (size_t i = 0; i < n; i++) lane_scalar_key(key, out, i);
+}
+
+void emu_sign(size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* rx, uint8_t* ry, uint8_t* s32, uint8_t* status) {
+    emu_init();
+    for (size_t i = 0; i < n; i++) lane_sign(key, msg, rx, ry, s32, status, i, g_comb);
+}
+
+uint32_t emu_compress(size_t n, const uint8_t* px, const uint8_t* py, uint8_t* out) {
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) lane_compress(px, py, out, i, flags);
+    return flags;
+}
+
+void emu_decompress(size_t n, const uint8_t* in, uint8_t* rx, uint8_t* ry, uint8_t* status) {
+    for (size_t i = 0; i < n; i++) lane_decompress(in, rx, ry, status, i);
+}
+
+uint32_t emu_poseidon(int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out) {
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) {
+        switch (n_inputs) {
+            case 1: lane_poseidon<2>(in, out, i, flags); break;
+            case 2: lane_poseidon<3>(in, out, i, flags); break;
+            case 3: lane_poseidon<4>(in, out, i, flags); break;
+            case 4: lane_poseidon<5>(in, out, i, flags); break;
+            case 5: lane_poseidon<6>(in, out, i, flags); break;
+            case 6: lane_poseidon<7>(in, out, i, flags); break;
+            case 7: lane_poseidon<8>(in, out, i, flags); break;
+            case 8: lane_poseidon<9>(in, out, i, flags); break;
+            default: return 0x80000000u;
+        }
+    }
+    return flags;
+}
+
+uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
+                    const uint8_t* ay, const uint8_t* msg, uint8_t* ok) {
+    emu_init();
+    uint32_t flags = 0;
+    for (size_t i = 0; i < n; i++) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, lane_table(), g_comb, flags);
+    return flags;
+}
+
+void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msg, uint8_t* ok,
+                           uint8_t* status) {
+    emu_init();
+    for (size_t i = 0; i < n; i++) lane_verify_compressed(sig64, pk32, msg, ok, status, i, lane_table(), g_comb);
+}
+
+}  // extern "C"

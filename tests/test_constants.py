@@ -1,0 +1,47 @@
+"""The product's build-time constant generator (babyjubjub-rs_b200/tools/gen_constants.py) and the
+oracle's (oracle/poseidon_constants.py) are independent implementations of the Grain LFSR; they must
+agree, and the emitted Montgomery constants must decode to the reference's values (src/lib.rs:28-58)."""
+import importlib.util
+import os
+import re
+
+from common import O, Q, ROOT
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("gen_constants", os.path.join(ROOT, "babyjubjub-rs_b200", "tools", "gen_constants.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_poseidon_tables_agree():
+    from oracle import poseidon_constants as pc
+    g = _gen()
+    for t in (2, 3, 6, 9):
+        rc, mds = g.poseidon_tables(t)
+        C, M = pc.constants(t)
+        assert rc == C and mds == M
+
+
+def test_emitted_constants_decode():
+    g = _gen()
+    inc = os.path.join(ROOT, "babyjubjub-rs_b200", "csrc", "generated", "bjj_consts.inc")
+    if not os.path.exists(inc):
+        g.main()
+    text = open(inc).read()
+    rinv = pow(1 << 256, -1, Q)
+
+    def const(name):
+        m = re.search(r"BJJ_%s\[8\] = \{([^}]*)\}" % name, text)
+        w = [int(x.strip().rstrip("u"), 16) for x in m.group(1).split(",")]
+        return sum(v << (32 * i) for i, v in enumerate(w))
+    assert const("Q") == Q and const("TWOQ") == 2 * Q and const("QHALF") == Q >> 1
+    assert const("ONE_M") * rinv % Q == 1
+    assert const("A_M") * rinv % Q == O.A and const("D_M") * rinv % Q == O.D
+    assert (const("B8X_M") * rinv % Q, const("B8Y_M") * rinv % Q) == O.B8
+    s = const("SQRT_NEG_A_M") * rinv % Q
+    assert (s * s + O.A) % Q == 0
+    assert const("INV_SQRT_NEG_A_M") * rinv % Q * s % Q == 1
+    assert const("SUBORDER") == O.SUBORDER and const("ORDER") == O.ORDER
+    assert const("TWO_DP_M") * rinv % Q == (-2 * O.D * pow(O.A, -1, Q)) % Q

@@ -1,0 +1,124 @@
+"""GPU parity through the C ABI (libbjj_cuda.so) against the oracle.  Bit-exact: this is integer work."""
+import numpy as np
+import pytest
+
+import parity
+from common import O, Q, pack, unpack
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fr(gpu, oracle_c):
+    parity.check_fr(gpu, oracle_c, 1 << 16)
+
+
+def test_add_affine(gpu, oracle_c):
+    parity.check_add(gpu, oracle_c, 1024)
+
+
+def test_mul_scalar(gpu, oracle_c):
+    parity.check_mul_scalar(gpu, oracle_c, 4096)
+
+
+def test_fixed_base_public(gpu, oracle_c):
+    parity.check_fixed_base(gpu, oracle_c, 4096)
+
+
+def test_compress_decompress(gpu, oracle_c):
+    parity.check_compress_decompress(gpu, oracle_c, 8192)
+
+
+def test_poseidon(gpu, oracle_c):
+    parity.check_poseidon(gpu, oracle_c, 512)
+
+
+def test_verify(gpu, oracle_c):
+    parity.check_verify(gpu, oracle_c, 64)
+
+
+def test_sign(gpu, oracle_c):
+    parity.check_sign(gpu, oracle_c, 256)
+
+
+def test_reference_api_mirror(gpu):
+    """the reference's own unit tests, re-expressed on the host mirror (src/lib.rs:420-738)"""
+    bjj = gpu.bjj
+    from common import KEY_KAT, MSG_KAT, P2_KAT, P_KAT
+    p = bjj.Point(*P_KAT)
+    r = p.projective().add(p.projective()).affine()                                   # test_add_same_point
+    assert (r.x, r.y) == (6890855772600357754907169075114257697580319025794532037257385534741338397365,
+                          4338620300185947561074059802482547481416142213883829469920100239455078257889)
+    r = p.projective().add(bjj.Point(*P2_KAT).projective()).affine()                  # test_add_different_points
+    assert (r.x, r.y) == (7916061937171219682591368294088513039687205273691143098332585753343424131937,
+                          14035240266687799601661095864649209771790948434046947201833777492504781204499)
+    m3 = p.mul_scalar(3)                                                              # test_mul_scalar
+    a3 = p.projective().add(p.projective()).add(p.projective()).affine()
+    assert m3.equals(a3)
+    assert m3.x == 19372461775513343691590086534037741906533799473648040012278229434133483800898
+    c = p.compress()                                                                  # test_point_compress_decompress
+    assert c.hex() == "53b81ed5bffe9545b54016234682e7b2f699bd42a5e9eae27ff4051bc698ce85"
+    assert bjj.decompress_point(c).equals(p)
+    with pytest.raises(ValueError, match="not a mod p square"):
+        bjj.decompress_point((1).to_bytes(32, "little"))
+    with pytest.raises(ValueError, match="y outside the Finite Field over R"):
+        bjj.decompress_point(Q.to_bytes(32, "little"))
+    sk = bjj.PrivateKey.import_(KEY_KAT)                                              # test_circomlib_testvector
+    assert sk.scalar_key() == 6466070937662820620902051049739362987537906109895538826186780010858059362905
+    pk = sk.public()
+    assert pk.x == 0x1d5ac1f31407018b7d413a4f52c8f74463b30e6ac2238220ad8b254de4eaa3a2
+    osig = O.sign(KEY_KAT, MSG_KAT)
+    sig = sk.sign(MSG_KAT)
+    assert (sig.r_b8.x, sig.r_b8.y, sig.s) == (osig[0][0], osig[0][1], osig[1])
+    with pytest.raises(ValueError, match="msg outside the Finite Field"):
+        sk.sign(Q + 1)
+    assert bjj.verify(pk, sig, MSG_KAT) is True
+    assert bjj.verify(pk, sig, MSG_KAT + 1) is False
+    sig2 = bjj.decompress_signature(sig.compress())                                   # test_signature_compress_decompress
+    assert sig2.r_b8.equals(sig.r_b8) and sig2.s == sig.s
+    assert bjj.verify_batch([pk, pk], [sig, sig2], [MSG_KAT, MSG_KAT + 2]) == [True, False]
+    pts = bjj.mul_scalar_batch([p, p], [3, 0])
+    assert pts[0].equals(m3) and (pts[1].x, pts[1].y) == (0, 1)
+    assert bjj.public_batch([sk])[0].equals(pk)
+    d = bjj.decompress_batch([c, (1).to_bytes(32, "little")])
+    assert d[0].equals(p) and isinstance(d[1], ValueError)
+
+
+def test_noncanonical_inputs_are_flagged(gpu):
+    bjj = gpu.bjj
+    a = pack([Q + 5, 3])
+    with pytest.raises(bjj.BjjError) as ei:
+        gpu.eng.fr_op_batch(bjj.FR_MUL, a, a)
+    assert ei.value.code == bjj.ERR_NONCANONICAL
+    # the flag is cleared by the failing call; the next call is clean
+    out = gpu.eng.fr_op_batch(bjj.FR_MUL, pack([2, 3]), pack([5, 7]))
+    assert unpack(out) == [10, 21]
+
+
+def test_empty_and_ragged_batches(gpu, oracle_c):
+    e = np.zeros((0, 32), dtype=np.uint8)
+    assert gpu.eng.verify_batch(e, e, e, e, e, e).shape == (0,)
+    assert gpu.eng.fixed_base_batch(e)[0].shape == (0, 32)
+    for n in (1, 31, 33, 127, 129, 1000):
+        k = pack([(i * 0x9E3779B97F4A7C15 + 12345) % (1 << 256) for i in range(n)])
+        got, exp = gpu.fixed_base(k), oracle_c.fixed_base(k)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+
+
+def test_large_batch_properties(gpu, oracle_c):
+    """size-independent checks at a chunk-crossing size: linearity of fixed-base, compress/decompress
+    round trip, and a sampled oracle comparison"""
+    n = (1 << 20) + 777            # crosses the 2^20-lane pipeline chunk
+    rng = np.random.default_rng(42)
+    k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    k[:, 31] &= 0x1F               # < 2^253
+    rx, ry = gpu.eng.fixed_base_batch(k)
+    comp = gpu.eng.compress_batch(rx, ry)
+    dx, dy, st = gpu.eng.decompress_batch(comp)
+    assert not st.any() and np.array_equal(dx, rx) and np.array_equal(dy, ry)
+    idx = rng.choice(n, size=512, replace=False)
+    ex, ey = oracle_c.fixed_base(k[idx])
+    assert np.array_equal(rx[idx], ex) and np.array_equal(ry[idx], ey)
+    # (k * B8) via the variable-base path must agree with the comb
+    b8x, b8y = pack([O.B8[0]] * 4096), pack([O.B8[1]] * 4096)
+    vx, vy = gpu.eng.mul_scalar_batch(b8x, b8y, k[:4096])
+    assert np.array_equal(vx, rx[:4096]) and np.array_equal(vy, ry[:4096])

@@ -1,0 +1,94 @@
+"""The oracle is pinned here: every known-answer vector the reference's tests hold for the hot path
+(reference src/lib.rs:420-552, 574-632, 688-738; src/utils.rs:229-260), the committed golden fixtures,
+and agreement between the two independent restatements (pure Python / C++)."""
+import json
+import os
+import random
+
+import numpy as np
+
+import parity
+from common import O, Q, pack, unpack
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_python_oracle_reproduces_reference_kats():
+    assert O.self_check()
+
+
+def test_poseidon_constants_anchors():
+    from oracle import poseidon_constants as pc
+    for t in range(2, 10):
+        C, M = pc.constants(t)          # asserts the anchors internally
+        assert len(C) == (8 + pc.R_P_TABLE[t - 2]) * t and len(M) == t
+
+
+def test_reference_kats_fixture():
+    """tests/golden/reference_kats.json transcribes the reference's own test vectors"""
+    with open(os.path.join(GOLDEN, "reference_kats.json")) as f:
+        g = json.load(f)
+    P = tuple(int(v) for v in g["P"])
+    P2 = tuple(int(v) for v in g["P2"])
+    assert O.proj_affine(O.proj_add(P + (1,), P + (1,))) == tuple(int(v) for v in g["P_plus_P"])
+    assert O.proj_affine(O.proj_add(P + (1,), P2 + (1,))) == tuple(int(v) for v in g["P_plus_P2"])
+    assert O.mul_scalar(P, 3) == tuple(int(v) for v in g["P_times_3"])
+    assert O.mul_scalar(P, int(g["n"])) == tuple(int(v) for v in g["P_times_n"])
+    assert O.compress(P).hex() == g["compress_P"]
+    for d in g["decompress"]:
+        assert O.decompress_point(bytes.fromhex(d["y_hex"]))[0] == int.from_bytes(bytes.fromhex(d["x_hex_le"]), "little")
+    c = g["circomlib"]
+    key = bytes.fromhex(c["key_hex"])
+    assert O.blake512(key).hex() == c["blake512_hex"]
+    assert O.scalar_key(key) == int(c["scalar_key"])
+    assert O.public(key) == (int(c["pk_x_hex"], 16), int(c["pk_y_hex"], 16))
+    msg = int.from_bytes(bytes.fromhex(c["msg_hex_le"]), "little")
+    sig = O.sign(key, msg)
+    assert sig == ((int(c["r8_x_hex"], 16), int(c["r8_y_hex"], 16)), int(c["s"]))
+    assert O.verify(O.public(key), sig, msg)
+    assert O.modinv(int(g["modinv"]["a"]), int(g["modinv"]["q"])) == int(g["modinv"]["inv"])
+    assert O.modsqrt(int(g["modsqrt"]["a"]), int(g["modsqrt"]["q"])) == int(g["modsqrt"]["root"])
+
+
+def test_edge_fixture_matches_oracles(oracle_c):
+    """tests/golden/edge_vectors.json (made by make_golden.py from the Python oracle) vs the C++ oracle"""
+    with open(os.path.join(GOLDEN, "edge_vectors.json")) as f:
+        g = json.load(f)
+    ms = g["mul_scalar"]
+    px, py, k = pack([int(c["px"]) for c in ms]), pack([int(c["py"]) for c in ms]), pack([int(c["k"]) for c in ms])
+    rx, ry = oracle_c.mul_scalar(px, py, k)
+    assert unpack(rx) == [int(c["rx"]) for c in ms] and unpack(ry) == [int(c["ry"]) for c in ms]
+    dc = g["decompress"]
+    C = np.frombuffer(b"".join(bytes.fromhex(c["in"]) for c in dc), dtype=np.uint8).reshape(-1, 32)
+    x, y, st = oracle_c.decompress(C)
+    assert list(st) == [c["status"] for c in dc]
+    assert unpack(x) == [int(c["x"]) for c in dc] and unpack(y) == [int(c["y"]) for c in dc]
+    vf = g["verify"]
+    arrs = [pack([int(c[f]) for c in vf]) for f in ("r8x", "r8y", "s", "ax", "ay", "msg")]
+    assert list(oracle_c.verify(*arrs)) == [c["ok"] for c in vf]
+    ps = g["poseidon"]
+    for c in ps:
+        ins = [pack([int(v)]) for v in c["in"]]
+        assert unpack(oracle_c.poseidon(ins))[0] == int(c["out"])
+
+
+def test_c_oracle_matches_python_oracle(oracle_c):
+    """the two restatements are independent implementations; they must agree lane for lane"""
+    class Py:
+        def fr_op(self, op, a, b):
+            f = {0: lambda x, y: x * y % Q, 1: lambda x, y: (x + y) % Q, 2: lambda x, y: (x - y) % Q,
+                 3: lambda x, y: pow(x, Q - 2, Q), 4: lambda x, y: x * x % Q}[op]
+            return pack([f(x, y) for x, y in zip(unpack(a), unpack(b))])
+    parity.check_fr(oracle_c, Py(), 200)
+    rnd = random.Random(11)
+    keys = [rnd.randbytes(32) for _ in range(4)]
+    msgs = [rnd.randrange(Q) for _ in range(4)]
+    rx, ry, s, _ = oracle_c.sign(np.frombuffer(b"".join(keys), dtype=np.uint8).reshape(-1, 32), pack(msgs))
+    exp = [O.sign(k, m) for k, m in zip(keys, msgs)]
+    assert list(zip(zip(unpack(rx), unpack(ry)), unpack(s))) == exp
+    # the parity helpers double as oracle-vs-oracle checks (they assert against the Python oracle inside)
+    parity.check_mul_scalar(oracle_c, oracle_c, 16)
+    parity.check_fixed_base(oracle_c, oracle_c, 8)
+    parity.check_compress_decompress(oracle_c, oracle_c, 40)
+    parity.check_poseidon(oracle_c, oracle_c, 4)
+    parity.check_verify(oracle_c, oracle_c, 2)
