@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "fr.cuh"
+#include "fr29_proto.cuh"
 
 using namespace bjj;
 
@@ -86,6 +87,36 @@ __global__ void k_fr_mul(uint32_t* out, int iters, uint32_t seed) {
     if (s == 0x1234567) out[0] = s;
 }
 
+template <int ILP, bool SQR>
+__global__ void k_fr29(uint32_t* out, int iters, uint32_t seed) {
+    bjj29::Fr29 x[ILP], y[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            x[k].v[i] = (seed + threadIdx.x * 977 + i * 131 + k) & bjj29::M29;
+            y[k].v[i] = (seed * 5 + blockIdx.x * 31 + i * 17 + k) & bjj29::M29;
+        }
+        x[k].v[8] &= 0xffffff;
+        y[k].v[8] &= 0xffffff;
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) {
+            if (SQR)
+                bjj29::sqr(x[k], x[k]);
+            else
+                bjj29::mul(x[k], x[k], y[k]);
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) s ^= x[k].v[i];
+    if (s == 0x1234567) out[0] = s;
+}
+
 template <class K>
 static float time_kernel(K launch, int reps) {
     cudaEvent_t e0, e1;
@@ -148,6 +179,22 @@ int main(int argc, char** argv) {
                    NAME, ILP, threads, per_sm, ms, fm / ms / 1e6, fm * 136.0 / ms / 1e9, fm * 136.0 / (ms * 1e-3) / model_peak); \
         }                                                                                                              \
     }
+#define FRB29(ILP, SQR, NAME)                                                                                          \
+    for (int threads : {128, 256}) {                                                                                   \
+        for (int per_sm : {1, 2, 4, 8}) {                                                                              \
+            if (threads * per_sm > 2048) continue;                                                                     \
+            const int grid = sms * per_sm;                                                                             \
+            const int iters = 2048;                                                                                    \
+            float ms = time_kernel([&]() { k_fr29<ILP, SQR><<<grid, threads>>>(out, iters, 777u); }, 3);               \
+            double fm = (double)grid * threads * iters * ILP;                                                          \
+            printf("{\"bench\": \"%s\", \"ilp\": %d, \"threads\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"gfmul_s\": %.2f}\n", \
+                   NAME, ILP, threads, per_sm, ms, fm / ms / 1e6);                                                     \
+        }                                                                                                              \
+    }
+    FRB29(1, false, "fr29_mul")
+    FRB29(2, false, "fr29_mul")
+    FRB29(1, true, "fr29_sqr")
+    FRB29(2, true, "fr29_sqr")
     FRB(1, false, "fr_mul")
     FRB(2, false, "fr_mul")
     FRB(4, false, "fr_mul")

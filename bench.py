@@ -246,8 +246,12 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     eng = bjj.Engine(local_rank)
     lib, ctx = eng.lib, eng.ctx
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the kernels are launched on it (passed to the _dev entry points) and the
+    # CUDA events that time them are recorded on the same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = ctypes.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     n = 1 << args.log2_lanes
 
     def dptr(t):
