@@ -67,11 +67,21 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_affine(size_t n, const uint8_t* p
 
 __global__ void __launch_bounds__(BJJ_BLOCK) k_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py,
                                                           const uint8_t* k, uint8_t* rx, uint8_t* ry, U128* table,
-                                                          uint32_t* gflags) {
+                                                          ExactQueue q, uint32_t* gflags) {
     BJJ_FLAGS_BEGIN
     const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_mul_scalar(px, py, k, rx, ry, i, tbl, flags);
+    BJJ_LANE_LOOP(n) lane_mul_scalar(px, py, k, rx, ry, i, tbl, q, flags);
     BJJ_FLAGS_END(gflags)
+}
+
+// exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queue of the fast kernel)
+#define BJJ_EXACT_BLOCK 64
+#define BJJ_QUEUE_LOOP(q) \
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *(q).count; j < cnt; j += gridDim.x * blockDim.x)
+
+__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* k,
+                                                                      uint8_t* rx, uint8_t* ry, ExactQueue q) {
+    BJJ_QUEUE_LOOP(q) lane_mul_scalar_exact(px, py, k, rx, ry, q.list[j]);
 }
 
 __global__ void __launch_bounds__(BJJ_BLOCK) k_fixed_base(size_t n, const uint8_t* k, uint8_t* rx, uint8_t* ry,
@@ -118,11 +128,17 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_poseidon(size_t n, PoseidonIn in,
 __global__ void __launch_bounds__(BJJ_BLOCK) k_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                       const uint8_t* s, const uint8_t* ax, const uint8_t* ay,
                                                       const uint8_t* msg, uint8_t* ok, U128* table,
-                                                      const CombEntry* comb, uint32_t* gflags) {
+                                                      const CombEntry* comb, ExactQueue q, uint32_t* gflags) {
     BJJ_FLAGS_BEGIN
     const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, tbl, comb, flags);
+    BJJ_LANE_LOOP(n) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, tbl, comb, q, flags);
     BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
+                                                                  const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
+                                                                  uint8_t* ok, ExactQueue q) {
+    BJJ_QUEUE_LOOP(q) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, q.list[j]);
 }
 
 __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32,
@@ -135,12 +151,20 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_compressed(size_t n, const
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
+// scratch that a launch needs besides its arguments: per-thread window tables and the exact-lane queue
+struct Workspace {
+    U128* table;
+    size_t table_slots;
+    uint32_t* exact_count;   // one device word
+    uint32_t* exact_list;
+    size_t exact_cap;
+};
+
 struct PipeSlot {
     cudaStream_t stream;
     uint8_t* arena;
     size_t arena_bytes;
-    U128* table;
-    size_t table_slots;
+    Workspace ws;
 };
 
 struct bjj_ctx {
@@ -148,8 +172,7 @@ struct bjj_ctx {
     int sms;
     cudaStream_t stream;        // stream of the _dev flavour when the caller passes NULL
     CombEntry* comb;
-    U128* table;                // per-thread window tables of the _dev flavour
-    size_t table_slots;
+    Workspace ws;               // workspace of the _dev flavour (host calls use their pipeline slot's)
     uint32_t* flags_dev;
     uint32_t* flags_host;       // pinned
     PipeSlot slot[BJJ_PIPE_SLOTS];
@@ -176,14 +199,37 @@ static int grid_for(bjj_ctx* ctx, const void* kernel, size_t n) {
     return (int)(want < cap ? want : cap);
 }
 
-static int ensure_table(bjj_ctx* ctx, U128** table, size_t* have, size_t slots) {
-    if (*have >= slots) return BJJ_OK;
-    if (*table) cudaFree(*table);
-    *table = nullptr;
-    *have = 0;
-    CU(ctx, cudaMalloc(table, slots * BJJ_TABLE_U128_PER_LANE * sizeof(U128)));
-    *have = slots;
+static int ensure_table(bjj_ctx* ctx, Workspace* ws, size_t slots) {
+    if (ws->table_slots >= slots) return BJJ_OK;
+    if (ws->table) cudaFree(ws->table);
+    ws->table = nullptr;
+    ws->table_slots = 0;
+    CU(ctx, cudaMalloc(&ws->table, slots * BJJ_TABLE_U128_PER_LANE * sizeof(U128)));
+    ws->table_slots = slots;
     return BJJ_OK;
+}
+
+// makes room for n queued lane indices and zeroes the counter on `st`
+static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, ExactQueue* q) {
+    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, sizeof(uint32_t)));
+    if (ws->exact_cap < n) {
+        if (ws->exact_list) cudaFree(ws->exact_list);
+        ws->exact_list = nullptr;
+        ws->exact_cap = 0;
+        CU(ctx, cudaMalloc(&ws->exact_list, n * sizeof(uint32_t)));
+        ws->exact_cap = n;
+    }
+    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, sizeof(uint32_t), st));
+    q->count = ws->exact_count;
+    q->list = ws->exact_list;
+    return BJJ_OK;
+}
+
+static void free_workspace(Workspace* ws) {
+    if (ws->table) cudaFree(ws->table);
+    if (ws->exact_count) cudaFree(ws->exact_count);
+    if (ws->exact_list) cudaFree(ws->exact_list);
+    memset(ws, 0, sizeof(*ws));
 }
 
 extern "C" {
@@ -260,10 +306,10 @@ void bjj_destroy(bjj_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int s = 0; s < BJJ_PIPE_SLOTS; s++) {
         if (ctx->slot[s].arena) cudaFree(ctx->slot[s].arena);
-        if (ctx->slot[s].table) cudaFree(ctx->slot[s].table);
+        free_workspace(&ctx->slot[s].ws);
         if (ctx->slot[s].stream) cudaStreamDestroy(ctx->slot[s].stream);
     }
-    if (ctx->table) cudaFree(ctx->table);
+    free_workspace(&ctx->ws);
     if (ctx->comb) cudaFree(ctx->comb);
     if (ctx->flags_dev) cudaFree(ctx->flags_dev);
     if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
@@ -342,29 +388,42 @@ int bjj_sync(bjj_ctx* ctx) {
 // `table`/`table_slots` select the per-thread window-table workspace (ctx-wide for _dev calls, per
 // pipeline slot for host calls).
 static int launch_mul_scalar(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
-                             uint8_t* rx, uint8_t* ry, cudaStream_t st, U128** table, size_t* slots) {
+                             uint8_t* rx, uint8_t* ry, cudaStream_t st, Workspace* ws) {
+    if (n >> 32) return BJJ_ERR_ARG;     // lane indices in the exact queue are 32-bit
     int grid = grid_for(ctx, (const void*)k_mul_scalar, n);
-    int rc = ensure_table(ctx, table, slots, (size_t)grid * BJJ_BLOCK);
+    int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
     if (rc) return rc;
-    k_mul_scalar<<<grid, BJJ_BLOCK, 0, st>>>(n, px, py, k, rx, ry, *table, ctx->flags_dev);
+    ExactQueue q;
+    rc = ensure_queue(ctx, ws, n, st, &q);
+    if (rc) return rc;
+    k_mul_scalar<<<grid, BJJ_BLOCK, 0, st>>>(n, px, py, k, rx, ry, ws->table, q, ctx->flags_dev);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    k_mul_scalar_exact<<<ctx->sms, BJJ_EXACT_BLOCK, 0, st>>>(px, py, k, rx, ry, q);
     DEV_EPILOGUE
 }
 static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                          const uint8_t* ax, const uint8_t* ay, const uint8_t* msg, uint8_t* ok, cudaStream_t st,
-                         U128** table, size_t* slots) {
+                         Workspace* ws) {
+    if (n >> 32) return BJJ_ERR_ARG;
     int grid = grid_for(ctx, (const void*)k_verify, n);
-    int rc = ensure_table(ctx, table, slots, (size_t)grid * BJJ_BLOCK);
+    int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
     if (rc) return rc;
-    k_verify<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s, ax, ay, msg, ok, *table, ctx->comb, ctx->flags_dev);
+    ExactQueue q;
+    rc = ensure_queue(ctx, ws, n, st, &q);
+    if (rc) return rc;
+    k_verify<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s, ax, ay, msg, ok, ws->table, ctx->comb, q, ctx->flags_dev);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    k_verify_exact<<<ctx->sms, BJJ_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, msg, ok, q);
     DEV_EPILOGUE
 }
 static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
-                                    const uint8_t* msg, uint8_t* ok, uint8_t* status, cudaStream_t st, U128** table,
-                                    size_t* slots) {
+                                    const uint8_t* msg, uint8_t* ok, uint8_t* status, cudaStream_t st, Workspace* ws) {
     int grid = grid_for(ctx, (const void*)k_verify_compressed, n);
-    int rc = ensure_table(ctx, table, slots, (size_t)grid * BJJ_BLOCK);
+    int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
     if (rc) return rc;
-    k_verify_compressed<<<grid, BJJ_BLOCK, 0, st>>>(n, sig64, pk32, msg, ok, status, *table, ctx->comb);
+    k_verify_compressed<<<grid, BJJ_BLOCK, 0, st>>>(n, sig64, pk32, msg, ok, status, ws->table, ctx->comb);
     DEV_EPILOGUE
 }
 static int launch_poseidon(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out,
@@ -423,7 +482,7 @@ int bjj_mul_scalar_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const ui
                              uint8_t* rx, uint8_t* ry, void* stream) {
     DEV_PROLOGUE
     if (!px || !py || !scalar32 || !rx || !ry) return BJJ_ERR_ARG;
-    return launch_mul_scalar(ctx, n, px, py, scalar32, rx, ry, st, &ctx->table, &ctx->table_slots);
+    return launch_mul_scalar(ctx, n, px, py, scalar32, rx, ry, st, &ctx->ws);
 }
 
 int bjj_fixed_base_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry, void* stream) {
@@ -482,14 +541,14 @@ int bjj_verify_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
                          const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, void* stream) {
     DEV_PROLOGUE
     if (!r8x || !r8y || !s32 || !ax || !ay || !msg32 || !ok) return BJJ_ERR_ARG;
-    return launch_verify(ctx, n, r8x, r8y, s32, ax, ay, msg32, ok, st, &ctx->table, &ctx->table_slots);
+    return launch_verify(ctx, n, r8x, r8y, s32, ax, ay, msg32, ok, st, &ctx->ws);
 }
 
 int bjj_verify_compressed_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
                                     const uint8_t* msg32, uint8_t* ok, uint8_t* status, void* stream) {
     DEV_PROLOGUE
     if (!sig64 || !pk32 || !msg32 || !ok || !status) return BJJ_ERR_ARG;
-    return launch_verify_compressed(ctx, n, sig64, pk32, msg32, ok, status, st, &ctx->table, &ctx->table_slots);
+    return launch_verify_compressed(ctx, n, sig64, pk32, msg32, ok, status, st, &ctx->ws);
 }
 
 }  // extern "C"
@@ -597,7 +656,7 @@ int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
     return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        return launch_mul_scalar(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.table, &sl.table_slots);
+        return launch_mul_scalar(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.ws);
     });
 }
 
@@ -671,7 +730,7 @@ int bjj_verify_batch(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* 
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(r8x, 32), H_IN(r8y, 32), H_IN(s32, 32), H_IN(ax, 32), H_IN(ay, 32), H_IN(msg32, 32), H_OUT(ok, 1)};
     return run_host(ctx, n, args, 7, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.table, &sl.table_slots);
+        return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.ws);
     });
 }
 
@@ -680,7 +739,7 @@ int bjj_verify_compressed_batch(bjj_ctx* ctx, size_t n, const uint8_t* sig64, co
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(sig64, 64), H_IN(pk32, 32), H_IN(msg32, 32), H_OUT(ok, 1), H_OUT(status, 1)};
     return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        return launch_verify_compressed(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.table, &sl.table_slots);
+        return launch_verify_compressed(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.ws);
     });
 }
 

@@ -326,25 +326,52 @@ BJJ_HD_NOINLINE void mul_scalar_exact(PointAff& r, const PointAff& p, const uint
     proj_affine(r, acc);
 }
 
-// Point::mul_scalar (src/lib.rs:149-164): on-curve gate -> fast ladder, else exact lane.
+// Queue of lanes that failed the on-curve gate.  The fast kernel only records their indices; a second,
+// small kernel replays the reference sequence for them, so the fast kernel carries neither the exact
+// path's registers nor its divergence.
+struct ExactQueue {
+    uint32_t* count;
+    uint32_t* list;
+};
+BJJ_HD void exact_push(const ExactQueue& q, size_t i) {
+#if BJJ_DEVICE_CODE
+    uint32_t slot = atomicAdd(q.count, 1u);
+#else
+    uint32_t slot = (*q.count)++;
+#endif
+    q.list[slot] = (uint32_t)i;
+}
+
+// Point::mul_scalar (src/lib.rs:149-164): on-curve gate -> fast ladder, else queued for the exact lane.
 BJJ_HD void lane_mul_scalar(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, uint8_t* rx,
-                            uint8_t* ry, size_t i, const LaneTable& tbl, uint32_t& flags) {
+                            uint8_t* ry, size_t i, const LaneTable& tbl, const ExactQueue& q, uint32_t& flags) {
     PointAff p;
+    load_fr(p.x, px, i, flags);
+    load_fr(p.y, py, i, flags);
+    if (!on_curve(p)) {
+        exact_push(q, i);
+        return;
+    }
+    uint32_t n[8];
+    load_u256(n, scalar, i);
+    PointExt e, acc;
+    ext_from_affine(e, p);
+    var_base_mul(acc, e, n, tbl);
+    store_ext_affine(rx, ry, i, acc);
+}
+
+// exact lane of mul_scalar: lane index taken from the queue
+BJJ_HD void lane_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, uint8_t* rx,
+                                  uint8_t* ry, size_t i) {
+    uint32_t flags = 0;
+    PointAff p, r;
     load_fr(p.x, px, i, flags);
     load_fr(p.y, py, i, flags);
     uint32_t n[8];
     load_u256(n, scalar, i);
-    if (on_curve(p)) {
-        PointExt e, acc;
-        ext_from_affine(e, p);
-        var_base_mul(acc, e, n, tbl);
-        store_ext_affine(rx, ry, i, acc);
-    } else {
-        PointAff r;
-        mul_scalar_exact(r, p, n, 8);
-        store_fr(rx, i, r.x);
-        store_fr(ry, i, r.y);
-    }
+    mul_scalar_exact(r, p, n, 8);
+    store_fr(rx, i, r.x);
+    store_fr(ry, i, r.y);
 }
 
 // B8.mul_scalar(k) for a raw 256-bit scalar (src/lib.rs:305, :329, :405)
@@ -598,9 +625,9 @@ BJJ_HD void lane_sign(const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, 
 //   accept iff  S*B8 == R8 + (8*hm)*A   compared in affine coordinates.
 // Fast lane (A and R8 on the curve): 8*hm*A = hm*(8A), so one Straus pass computes
 //   P = S*B8 + hm*(-8A)  and the test is  P == R8  checked projectively (no inversion).
-// Exact lane (any input point off the curve): the reference sequence replayed literally.
-BJJ_HD uint32_t verify_core(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m,
-                            const LaneTable& tbl, const CombEntry* comb) {
+// Exact lane (any input point off the curve): the reference sequence replayed literally, in a second
+// kernel fed by the ExactQueue.
+BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& msg_m) {
     Fr st[6];
     fr_zero(st[0]);
     st[1] = r8.x;
@@ -609,53 +636,62 @@ BJJ_HD uint32_t verify_core(const PointAff& r8, const uint32_t* s, const PointAf
     st[4] = a.y;
     st[5] = msg_m;
     poseidon_permute<6>(st);
-    Fr hm;
     fr_from_mont(hm, st[0]);      // canonical integer hm < Q
-    if (on_curve(a) && on_curve(r8)) {
-        PointExt pa, acc;
-        ext_from_affine(pa, a);
-        ext_dbl<false>(pa, pa);
-        ext_dbl<false>(pa, pa);
-        ext_dbl<true>(pa, pa);
-        // negate: (-X, Y, Z, -T)
-        fr_neg(pa.X, pa.X);
-        fr_neg(pa.T, pa.T);
-        table_build(tbl, pa);
-        Recode4 ra;
-        recode4(ra, hm.v);
-        Recode8 rs;
-        recode8(rs, s);
-        ext_identity(acc);
-        Niels nn;
-        NielsAff nb;
-        table_select(nn, tbl, (int)ra.top);
-        ext_add_niels<true>(acc, acc, nn);
-        comb_select(nb, comb, 0, (int)rs.top);
-        ext_add_niels_aff<false>(acc, acc, nb);
+}
+
+// requires A and R8 ON the curve
+BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m,
+                            const LaneTable& tbl, const CombEntry* comb) {
+    Fr hm;
+    verify_hm(hm, r8, a, msg_m);
+    PointExt pa, acc;
+    ext_from_affine(pa, a);
+    ext_dbl<false>(pa, pa);
+    ext_dbl<false>(pa, pa);
+    ext_dbl<true>(pa, pa);
+    // negate: (-X, Y, Z, -T)
+    fr_neg(pa.X, pa.X);
+    fr_neg(pa.T, pa.T);
+    table_build(tbl, pa);
+    Recode4 ra;
+    recode4(ra, hm.v);
+    Recode8 rs;
+    recode8(rs, s);
+    ext_identity(acc);
+    Niels nn;
+    NielsAff nb;
+    table_select(nn, tbl, (int)ra.top);
+    ext_add_niels<true>(acc, acc, nn);
+    comb_select(nb, comb, 0, (int)rs.top);
+    ext_add_niels_aff<false>(acc, acc, nb);
 #pragma unroll 1
-        for (int i = 63; i >= 0; i--) {
-            ext_dbl<false>(acc, acc);
-            ext_dbl<false>(acc, acc);
-            ext_dbl<false>(acc, acc);
-            ext_dbl<true>(acc, acc);
-            table_select(nn, tbl, recode4_digit(ra, i));
-            if (i & 1) {
-                ext_add_niels<false>(acc, acc, nn);
-            } else {
-                ext_add_niels<true>(acc, acc, nn);
-                comb_select(nb, comb, 0, recode8_digit(rs, i >> 1));
-                ext_add_niels_aff<false>(acc, acc, nb);
-            }
+    for (int i = 63; i >= 0; i--) {
+        ext_dbl<false>(acc, acc);
+        ext_dbl<false>(acc, acc);
+        ext_dbl<false>(acc, acc);
+        ext_dbl<true>(acc, acc);
+        table_select(nn, tbl, recode4_digit(ra, i));
+        if (i & 1) {
+            ext_add_niels<false>(acc, acc, nn);
+        } else {
+            ext_add_niels<true>(acc, acc, nn);
+            comb_select(nb, comb, 0, recode8_digit(rs, i >> 1));
+            ext_add_niels_aff<false>(acc, acc, nb);
         }
-        // acc == R8 ?   X = x_R8 * sqrt(-a) * Z   and   Y = y_R8 * Z     (Z != 0: complete formulas)
-        const Fr sq = fr_const(BJJ_SQRT_NEG_A_M);
-        Fr lx, ly;
-        fr_mul(lx, r8.x, sq);
-        fr_mul(lx, lx, acc.Z);
-        fr_mul(ly, r8.y, acc.Z);
-        return (fr_eq(lx, acc.X) && fr_eq(ly, acc.Y)) ? 1u : 0u;
     }
-    // exact lane
+    // acc == R8 ?   X = x_R8 * sqrt(-a) * Z   and   Y = y_R8 * Z     (Z != 0: complete formulas)
+    const Fr sq = fr_const(BJJ_SQRT_NEG_A_M);
+    Fr lx, ly;
+    fr_mul(lx, r8.x, sq);
+    fr_mul(lx, lx, acc.Z);
+    fr_mul(ly, r8.y, acc.Z);
+    return (fr_eq(lx, acc.X) && fr_eq(ly, acc.Y)) ? 1u : 0u;
+}
+
+// any A / R8 (also off the curve): src/lib.rs:395-412 operation for operation
+BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m) {
+    Fr hm;
+    verify_hm(hm, r8, a, msg_m);
     PointAff b8, l, ka, ra;
     b8.x = fr_const(BJJ_B8X_M);
     b8.y = fr_const(BJJ_B8Y_M);
@@ -678,31 +714,59 @@ BJJ_HD uint32_t verify_core(const PointAff& r8, const uint32_t* s, const PointAf
     return (fr_eq(l.x, ra.x) && fr_eq(l.y, ra.y)) ? 1u : 0u;
 }
 
-BJJ_HD void lane_verify(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
-                        const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i, const LaneTable& tbl,
-                        const CombEntry* comb, uint32_t& flags) {
-    uint32_t msg[8], s[8];
+// loads one verify lane; returns false when msg > Q (reference: `false` before anything else, src/lib.rs:396)
+BJJ_HD bool verify_load(PointAff& r8, uint32_t* s, PointAff& a, Fr& mm, const uint8_t* r8x, const uint8_t* r8y,
+                        const uint8_t* s32, const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, size_t i,
+                        uint32_t& flags) {
+    uint32_t msg[8];
     load_u256(msg, msg32, i);
     const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
-    if (u256_lt(q, msg)) {     // msg > Q -> false; msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
-        ok[i] = 0;
-        return;
-    }
+    if (u256_lt(q, msg)) return false;     // msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
     load_u256(s, s32, i);
-    PointAff r8, a;
     load_fr(r8.x, r8x, i, flags);
     load_fr(r8.y, r8y, i, flags);
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
-    Fr mraw, mm;
+    Fr mraw;
     fr_set(mraw, msg);
     fr_to_mont(mm, mraw);
-    ok[i] = (uint8_t)verify_core(r8, s, a, mm, tbl, comb);
+    return true;
+}
+
+BJJ_HD void lane_verify(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
+                        const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i, const LaneTable& tbl,
+                        const CombEntry* comb, const ExactQueue& q, uint32_t& flags) {
+    uint32_t s[8];
+    PointAff r8, a;
+    Fr mm;
+    if (!verify_load(r8, s, a, mm, r8x, r8y, s32, ax, ay, msg32, i, flags)) {
+        ok[i] = 0;
+        return;
+    }
+    if (!(on_curve(a) && on_curve(r8))) {
+        ok[i] = 0;
+        exact_push(q, i);
+        return;
+    }
+    ok[i] = (uint8_t)verify_fast(r8, s, a, mm, tbl, comb);
+}
+
+BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
+                              const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i) {
+    uint32_t s[8], flags = 0;
+    PointAff r8, a;
+    Fr mm;
+    if (!verify_load(r8, s, a, mm, r8x, r8y, s32, ax, ay, msg32, i, flags)) {
+        ok[i] = 0;
+        return;
+    }
+    ok[i] = (uint8_t)verify_exact(r8, s, a, mm);
 }
 
 // decompress_signature + decompress(pk) + verify (src/lib.rs:260-268, 192-224, 395-412):
 // sig64 = compress(R8) || S_le32, pk32 = compress(A).  status = first decompression error (R8 first,
-// then A), ok = 0 whenever status != 0.
+// then A), ok = 0 whenever status != 0.  Decompressed points are on the curve by construction, so this
+// pipeline never needs the exact lane.
 BJJ_HD void lane_verify_compressed(const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msg32, uint8_t* ok,
                                    uint8_t* status, size_t i, const LaneTable& tbl, const CombEntry* comb) {
     uint32_t rb[8], s[8], ab[8], msg[8];
@@ -726,7 +790,7 @@ BJJ_HD void lane_verify_compressed(const uint8_t* sig64, const uint8_t* pk32, co
     Fr mraw, mm;
     fr_set(mraw, msg);
     fr_to_mont(mm, mraw);
-    ok[i] = (uint8_t)verify_core(r8, s, a, mm, tbl, comb);
+    ok[i] = (uint8_t)verify_fast(r8, s, a, mm, tbl, comb);
 }
 
 }  // namespace bjj

@@ -15,6 +15,17 @@ using namespace bjj;
 static CombEntry* g_comb = nullptr;
 static std::vector<U128> g_table(BJJ_TABLE_U128_PER_LANE);
 
+static std::vector<uint32_t> g_list;
+static uint32_t g_count;
+static ExactQueue exact_queue(size_t n) {
+    g_list.assign(n + 1, 0);
+    g_count = 0;
+    ExactQueue q;
+    q.count = &g_count;
+    q.list = g_list.data();
+    return q;
+}
+
 static LaneTable lane_table() {
     LaneTable t;
     t.base = g_table.data();
@@ -72,7 +83,9 @@ uint32_t emu_affine(size_t n, const uint8_t* px, const uint8_t* py, const uint8_
 
 uint32_t emu_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx, uint8_t* ry) {
     uint32_t flags = 0;
-    for (size_t i = 0; i < n; i++) lane_mul_scalar(px, py, k, rx, ry, i, lane_table(), flags);
+    ExactQueue q = exact_queue(n);
+    for (size_t i = 0; i < n; i++) lane_mul_scalar(px, py, k, rx, ry, i, lane_table(), q, flags);
+    for (uint32_t j = 0; j < g_count; j++) lane_mul_scalar_exact(px, py, k, rx, ry, g_list[j]);
     return flags;
 }
 
@@ -127,7 +140,9 @@ uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint
                     const uint8_t* ay, const uint8_t* msg, uint8_t* ok) {
     emu_init();
     uint32_t flags = 0;
-    for (size_t i = 0; i < n; i++) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, lane_table(), g_comb, flags);
+    ExactQueue q = exact_queue(n);
+    for (size_t i = 0; i < n; i++) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, lane_table(), g_comb, q, flags);
+    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, g_list[j]);
     return flags;
 }
 
