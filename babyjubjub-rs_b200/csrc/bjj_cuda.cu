@@ -10,31 +10,16 @@
 #include <string.h>
 
 #include "../../include/bjj_cuda.h"
-#include "lanes.cuh"
+#include "kernels.h"
 
 using namespace bjj;
 
-#define BJJ_BLOCK 128
 #define BJJ_PIPE_SLOTS 2
 #define BJJ_CHUNK_LANES (1u << 20)
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-#define BJJ_LANE_LOOP(n) \
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
-#define BJJ_FLAGS_BEGIN uint32_t flags = 0;
-#define BJJ_FLAGS_END(p) \
-    if (flags) atomicOr(p, flags);
-
-__device__ __forceinline__ LaneTable thread_table(U128* base) {
-    LaneTable t;
-    t.base = base;
-    t.stride = (size_t)gridDim.x * blockDim.x;
-    t.slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    return t;
-}
-
 __global__ void __launch_bounds__(BJJ_BLOCK) k_comb_build(CombEntry* comb) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES) return;
@@ -65,38 +50,19 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_affine(size_t n, const uint8_t* p
     BJJ_FLAGS_END(gflags)
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK) k_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py,
-                                                          const uint8_t* k, uint8_t* rx, uint8_t* ry, U128* table,
-                                                          ExactQueue q, uint32_t* gflags) {
-    BJJ_FLAGS_BEGIN
-    const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_mul_scalar(px, py, k, rx, ry, i, tbl, q, flags);
-    BJJ_FLAGS_END(gflags)
+// projective scratch -> canonical affine outputs, one Fermat inversion per THREAD (Montgomery's trick)
+__global__ void __launch_bounds__(BJJ_BLOCK) k_batch_affine(size_t n, ProjScratch scr, uint8_t* rx, uint8_t* ry) {
+    batch_affine_strided(scr, rx, ry, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
-// exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queue of the fast kernel)
-#define BJJ_EXACT_BLOCK 64
-#define BJJ_QUEUE_LOOP(q) \
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *(q).count; j < cnt; j += gridDim.x * blockDim.x)
-
-__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* k,
-                                                                      uint8_t* rx, uint8_t* ry, ExactQueue q) {
-    BJJ_QUEUE_LOOP(q) lane_mul_scalar_exact(px, py, k, rx, ry, q.list[j]);
-}
-
-__global__ void __launch_bounds__(BJJ_BLOCK) k_fixed_base(size_t n, const uint8_t* k, uint8_t* rx, uint8_t* ry,
+__global__ void __launch_bounds__(BJJ_BLOCK) k_fixed_base(size_t n, const uint8_t* k, ProjScratch scr,
                                                           const CombEntry* comb) {
-    BJJ_LANE_LOOP(n) lane_fixed_base(k, rx, ry, i, comb);
+    BJJ_LANE_LOOP(n) lane_fixed_base(k, scr, i, comb);
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK) k_public(size_t n, const uint8_t* key, uint8_t* rx, uint8_t* ry,
+__global__ void __launch_bounds__(BJJ_BLOCK) k_public(size_t n, const uint8_t* key, ProjScratch scr,
                                                       const CombEntry* comb) {
-    BJJ_LANE_LOOP(n) lane_public(key, rx, ry, i, comb);
-}
-
-__global__ void __launch_bounds__(BJJ_BLOCK) k_sign(size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* r8x,
-                                                    uint8_t* r8y, uint8_t* s32, uint8_t* status, const CombEntry* comb) {
-    BJJ_LANE_LOOP(n) lane_sign(key, msg, r8x, r8y, s32, status, i, comb);
+    BJJ_LANE_LOOP(n) lane_public(key, scr, i, comb);
 }
 
 __global__ void __launch_bounds__(BJJ_BLOCK) k_scalar_key(size_t n, const uint8_t* key, uint8_t* out) {
@@ -115,39 +81,6 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_decompress(size_t n, const uint8_
     BJJ_LANE_LOOP(n) lane_decompress(in, rx, ry, status, i);
 }
 
-struct PoseidonIn {
-    const uint8_t* p[8];
-};
-template <int T>
-__global__ void __launch_bounds__(BJJ_BLOCK) k_poseidon(size_t n, PoseidonIn in, uint8_t* out, uint32_t* gflags) {
-    BJJ_FLAGS_BEGIN
-    BJJ_LANE_LOOP(n) lane_poseidon<T>(in.p, out, i, flags);
-    BJJ_FLAGS_END(gflags)
-}
-
-__global__ void __launch_bounds__(BJJ_BLOCK) k_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y,
-                                                      const uint8_t* s, const uint8_t* ax, const uint8_t* ay,
-                                                      const uint8_t* msg, uint8_t* ok, U128* table,
-                                                      const CombEntry* comb, ExactQueue q, uint32_t* gflags) {
-    BJJ_FLAGS_BEGIN
-    const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, tbl, comb, q, flags);
-    BJJ_FLAGS_END(gflags)
-}
-
-__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
-                                                                  const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
-                                                                  uint8_t* ok, ExactQueue q) {
-    BJJ_QUEUE_LOOP(q) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, q.list[j]);
-}
-
-__global__ void __launch_bounds__(BJJ_BLOCK) k_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32,
-                                                                 const uint8_t* msg, uint8_t* ok, uint8_t* status,
-                                                                 U128* table, const CombEntry* comb) {
-    const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_verify_compressed(sig64, pk32, msg, ok, status, i, tbl, comb);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
@@ -158,6 +91,12 @@ struct Workspace {
     uint32_t* exact_count;   // one device word
     uint32_t* exact_list;
     size_t exact_cap;
+    uint8_t* proj;           // 4 x 32 B per lane: X, Y, Z, running product
+    size_t proj_lanes;
+    uint8_t* vs;             // verify scratch: hm + decompressed R8, A (5 x 32 B per lane)
+    size_t vs_lanes;
+    cudaStream_t aux;        // side stream: the exact-lane kernel overlaps the fast EC kernel
+    cudaEvent_t ev_fork, ev_join;
 };
 
 struct PipeSlot {
@@ -199,6 +138,13 @@ static int grid_for(bjj_ctx* ctx, const void* kernel, size_t n) {
     return (int)(want < cap ? want : cap);
 }
 
+static int grid_cap(bjj_ctx* ctx, int per_sm, size_t n) {
+    size_t want = (n + BJJ_BLOCK - 1) / BJJ_BLOCK;
+    size_t cap = (size_t)ctx->sms * (per_sm < 1 ? 1 : per_sm);
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
 static int ensure_table(bjj_ctx* ctx, Workspace* ws, size_t slots) {
     if (ws->table_slots >= slots) return BJJ_OK;
     if (ws->table) cudaFree(ws->table);
@@ -225,8 +171,52 @@ static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, 
     return BJJ_OK;
 }
 
+// sub-batch size of the point kernels: bounds the projective scratch at 4 x 32 B x 2^21 = 256 MiB
+#define BJJ_POINT_SUBBATCH ((size_t)1 << 21)
+
+static int ensure_proj(bjj_ctx* ctx, Workspace* ws, size_t lanes, ProjScratch* scr) {
+    if (ws->proj_lanes < lanes) {
+        if (ws->proj) cudaFree(ws->proj);
+    if (ws->vs) cudaFree(ws->vs);
+        ws->proj = nullptr;
+        ws->proj_lanes = 0;
+        CU(ctx, cudaMalloc(&ws->proj, lanes * 128));
+        ws->proj_lanes = lanes;
+    }
+    scr->x = ws->proj;
+    scr->y = scr->x + 32 * ws->proj_lanes;
+    scr->z = scr->y + 32 * ws->proj_lanes;
+    scr->p = scr->z + 32 * ws->proj_lanes;
+    return BJJ_OK;
+}
+
+// grid of the batched affine pass: every thread should own >= 32 lanes so its one Fermat inversion
+// (~380 fmul) is amortised, but never more threads than the device holds at once
+static int affine_grid(bjj_ctx* ctx, size_t n) {
+    size_t want = (n / 32 + BJJ_BLOCK - 1) / BJJ_BLOCK;
+    size_t cap = (size_t)ctx->sms * 8;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+static int ensure_aux(bjj_ctx* ctx, Workspace* ws) {
+    if (ws->aux) return BJJ_OK;
+    CU(ctx, cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming));
+    return BJJ_OK;
+}
+
 static void free_workspace(Workspace* ws) {
+    if (ws->aux) {
+        cudaStreamSynchronize(ws->aux);
+        cudaEventDestroy(ws->ev_fork);
+        cudaEventDestroy(ws->ev_join);
+        cudaStreamDestroy(ws->aux);
+    }
     if (ws->table) cudaFree(ws->table);
+    if (ws->proj) cudaFree(ws->proj);
+    if (ws->vs) cudaFree(ws->vs);
     if (ws->exact_count) cudaFree(ws->exact_count);
     if (ws->exact_list) cudaFree(ws->exact_list);
     memset(ws, 0, sizeof(*ws));
@@ -389,65 +379,137 @@ int bjj_sync(bjj_ctx* ctx) {
 // pipeline slot for host calls).
 static int launch_mul_scalar(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
                              uint8_t* rx, uint8_t* ry, cudaStream_t st, Workspace* ws) {
-    if (n >> 32) return BJJ_ERR_ARG;     // lane indices in the exact queue are 32-bit
-    int grid = grid_for(ctx, (const void*)k_mul_scalar, n);
-    int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
-    if (rc) return rc;
-    ExactQueue q;
-    rc = ensure_queue(ctx, ws, n, st, &q);
-    if (rc) return rc;
-    k_mul_scalar<<<grid, BJJ_BLOCK, 0, st>>>(n, px, py, k, rx, ry, ws->table, q, ctx->flags_dev);
-    ctx->launches++;
-    CU(ctx, cudaGetLastError());
-    k_mul_scalar_exact<<<ctx->sms, BJJ_EXACT_BLOCK, 0, st>>>(px, py, k, rx, ry, q);
-    DEV_EPILOGUE
+    for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
+        const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
+        const size_t o = 32 * off;
+        int grid = grid_cap(ctx, bjjk::mul_scalar_blocks_per_sm(), m);
+        int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
+        if (rc) return rc;
+        ExactQueue q;
+        rc = ensure_queue(ctx, ws, m, st, &q);
+        if (rc) return rc;
+        ProjScratch scr;
+        rc = ensure_proj(ctx, ws, m < BJJ_POINT_SUBBATCH && n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &scr);
+        if (rc) return rc;
+        bjjk::mul_scalar(grid, st, m, px + o, py + o, k + o, scr, ws->table, q, ctx->flags_dev);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        k_batch_affine<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr, rx + o, ry + o);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        bjjk::mul_scalar_exact(ctx->sms * 4, st, px + o, py + o, k + o, rx + o, ry + o, q);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return BJJ_OK;
 }
+// fixed-base flavours: `from_keys` selects PrivateKey::public (BLAKE-512 + prune + >>3 first)
+static int launch_fixed_base(bjj_ctx* ctx, size_t n, const uint8_t* in, uint8_t* rx, uint8_t* ry, bool from_keys,
+                             cudaStream_t st, Workspace* ws) {
+    for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
+        const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
+        const size_t o = 32 * off;
+        ProjScratch scr;
+        int rc = ensure_proj(ctx, ws, m < BJJ_POINT_SUBBATCH && n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &scr);
+        if (rc) return rc;
+        if (from_keys)
+            k_public<<<grid_for(ctx, (const void*)k_public, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb);
+        else
+            k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        k_batch_affine<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr, rx + o, ry + o);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return BJJ_OK;
+}
+// verify scratch: hm (32 B / lane) and, for the compressed pipeline, the four decompressed coordinates
+static int ensure_vscratch(bjj_ctx* ctx, Workspace* ws, size_t lanes, uint8_t** hm, uint8_t** pts) {
+    if (ws->vs_lanes < lanes) {
+        if (ws->vs) cudaFree(ws->vs);
+        ws->vs = nullptr;
+        ws->vs_lanes = 0;
+        CU(ctx, cudaMalloc(&ws->vs, lanes * 160));
+        ws->vs_lanes = lanes;
+    }
+    *hm = ws->vs;
+    *pts = ws->vs + 32 * ws->vs_lanes;
+    return BJJ_OK;
+}
+
 static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                          const uint8_t* ax, const uint8_t* ay, const uint8_t* msg, uint8_t* ok, cudaStream_t st,
                          Workspace* ws) {
-    if (n >> 32) return BJJ_ERR_ARG;
-    int grid = grid_for(ctx, (const void*)k_verify, n);
-    int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
-    if (rc) return rc;
-    ExactQueue q;
-    rc = ensure_queue(ctx, ws, n, st, &q);
-    if (rc) return rc;
-    k_verify<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s, ax, ay, msg, ok, ws->table, ctx->comb, q, ctx->flags_dev);
-    ctx->launches++;
-    CU(ctx, cudaGetLastError());
-    k_verify_exact<<<ctx->sms, BJJ_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, msg, ok, q);
-    DEV_EPILOGUE
+    for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
+        const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
+        const size_t o = 32 * off;
+        const int grid_h = grid_cap(ctx, bjjk::verify_hash_blocks_per_sm(), m);
+        const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
+        int rc = ensure_table(ctx, ws, (size_t)grid_e * BJJ_BLOCK);
+        if (rc) return rc;
+        ExactQueue q;
+        rc = ensure_queue(ctx, ws, m, st, &q);
+        if (rc) return rc;
+        uint8_t *hm, *pts;
+        rc = ensure_vscratch(ctx, ws, n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &hm, &pts);
+        if (rc) return rc;
+        rc = ensure_aux(ctx, ws);
+        if (rc) return rc;
+        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, nullptr, hm, ok + off, true, q, ctx->flags_dev);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        // the queue is complete: the (slow, rare) exact lanes run on the side stream, concurrently with the
+        // Straus kernel; both write disjoint ok[] lanes
+        CU(ctx, cudaEventRecord(ws->ev_fork, st));
+        CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+        bjjk::verify_exact(ctx->sms * 4, ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, msg + o, ok + off, q, ctx->comb);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
+        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, s + o, 1, 0, ax + o, ay + o, hm, ok + off, ws->table, ctx->comb);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
+    }
+    return BJJ_OK;
 }
 static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
                                     const uint8_t* msg, uint8_t* ok, uint8_t* status, cudaStream_t st, Workspace* ws) {
-    int grid = grid_for(ctx, (const void*)k_verify_compressed, n);
-    int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
-    if (rc) return rc;
-    k_verify_compressed<<<grid, BJJ_BLOCK, 0, st>>>(n, sig64, pk32, msg, ok, status, ws->table, ctx->comb);
-    DEV_EPILOGUE
+    for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
+        const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
+        const size_t o = 32 * off;
+        const int grid_h = grid_cap(ctx, bjjk::verify_hash_blocks_per_sm(), m);
+        const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
+        int rc = ensure_table(ctx, ws, (size_t)grid_e * BJJ_BLOCK);
+        if (rc) return rc;
+        ExactQueue q;     // never fed here (decompressed points are on the curve) but the kernel wants a valid one
+        rc = ensure_queue(ctx, ws, 1, st, &q);
+        if (rc) return rc;
+        uint8_t *hm, *pts;
+        rc = ensure_vscratch(ctx, ws, n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &hm, &pts);
+        if (rc) return rc;
+        const size_t L = 32 * ws->vs_lanes;
+        uint8_t *dx = pts, *dy = pts + L, *dax = pts + 2 * L, *day = pts + 3 * L;
+        bjjk::decompress_pair(grid_cap(ctx, bjjk::decompress_pair_blocks_per_sm(), m), st, m, sig64 + 2 * o, pk32 + o, dx, dy,
+                              dax, day, status + off);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, ctx->flags_dev);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        bjjk::verify_ec(grid_e, st, m, dx, dy, sig64 + 2 * o, 2, 1, dax, day, hm, ok + off, ws->table, ctx->comb);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return BJJ_OK;
 }
 static int launch_poseidon(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out,
                            cudaStream_t st) {
     PoseidonIn pin;
     for (int j = 0; j < 8; j++) pin.p[j] = j < n_inputs ? in[j] : nullptr;
-#define POS_CASE(T_)                                                                              \
-    case T_ - 1: {                                                                                \
-        int grid = grid_for(ctx, (const void*)k_poseidon<T_>, n);                                 \
-        k_poseidon<T_><<<grid, BJJ_BLOCK, 0, st>>>(n, pin, out, ctx->flags_dev);                  \
-        break;                                                                                    \
-    }
-    switch (n_inputs) {
-        POS_CASE(2)
-        POS_CASE(3)
-        POS_CASE(4)
-        POS_CASE(5)
-        POS_CASE(6)
-        POS_CASE(7)
-        POS_CASE(8)
-        POS_CASE(9)
-        default: return BJJ_ERR_ARG;
-    }
-#undef POS_CASE
+    if (n_inputs < 1 || n_inputs > 8) return BJJ_ERR_ARG;
+    bjjk::poseidon(n_inputs + 1, grid_cap(ctx, bjjk::poseidon_blocks_per_sm(n_inputs + 1), n), st, n, pin, out, ctx->flags_dev);
     DEV_EPILOGUE
 }
 
@@ -488,22 +550,20 @@ int bjj_mul_scalar_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const ui
 int bjj_fixed_base_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry, void* stream) {
     DEV_PROLOGUE
     if (!scalar32 || !rx || !ry) return BJJ_ERR_ARG;
-    k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, n), BJJ_BLOCK, 0, st>>>(n, scalar32, rx, ry, ctx->comb);
-    DEV_EPILOGUE
+    return launch_fixed_base(ctx, n, scalar32, rx, ry, false, st, &ctx->ws);
 }
 
 int bjj_public_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* rx, uint8_t* ry, void* stream) {
     DEV_PROLOGUE
     if (!key32 || !rx || !ry) return BJJ_ERR_ARG;
-    k_public<<<grid_for(ctx, (const void*)k_public, n), BJJ_BLOCK, 0, st>>>(n, key32, rx, ry, ctx->comb);
-    DEV_EPILOGUE
+    return launch_fixed_base(ctx, n, key32, rx, ry, true, st, &ctx->ws);
 }
 
 int bjj_sign_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, uint8_t* r8y,
                        uint8_t* s32, uint8_t* status, void* stream) {
     DEV_PROLOGUE
     if (!key32 || !msg32 || !r8x || !r8y || !s32 || !status) return BJJ_ERR_ARG;
-    k_sign<<<grid_for(ctx, (const void*)k_sign, n), BJJ_BLOCK, 0, st>>>(n, key32, msg32, r8x, r8y, s32, status, ctx->comb);
+    bjjk::sign(grid_cap(ctx, bjjk::sign_blocks_per_sm(), n), st, n, key32, msg32, r8x, r8y, s32, status, ctx->comb);
     DEV_EPILOGUE
 }
 
@@ -664,8 +724,7 @@ int bjj_fixed_base_batch(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
     return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], ctx->comb);
-        CHECK_LAUNCH(ctx)
+        return launch_fixed_base(ctx, m, d[0], d[1], d[2], false, sl.stream, &sl.ws);
     });
 }
 
@@ -673,8 +732,7 @@ int bjj_public_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* rx, 
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(key32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
     return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        k_public<<<grid_for(ctx, (const void*)k_public, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], ctx->comb);
-        CHECK_LAUNCH(ctx)
+        return launch_fixed_base(ctx, m, d[0], d[1], d[2], true, sl.stream, &sl.ws);
     });
 }
 
@@ -683,7 +741,7 @@ int bjj_sign_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* 
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(key32, 32), H_IN(msg32, 32), H_OUT(r8x, 32), H_OUT(r8y, 32), H_OUT(s32, 32), H_OUT(status, 1)};
     return run_host(ctx, n, args, 6, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        k_sign<<<grid_for(ctx, (const void*)k_sign, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4], d[5], ctx->comb);
+        bjjk::sign(grid_cap(ctx, bjjk::sign_blocks_per_sm(), m), sl.stream, m, d[0], d[1], d[2], d[3], d[4], d[5], ctx->comb);
         CHECK_LAUNCH(ctx)
     });
 }

@@ -1,0 +1,80 @@
+// verify_batch / verify_compressed_batch kernels (reference: verify, src/lib.rs:395-412; decompress_signature
+// + decompress_point, src/lib.rs:260-268, 192-224).  The lane bodies are in lanes.cuh.
+//
+// One verification is a short pipeline of kernels, so that no kernel carries another phase's registers
+// or instruction footprint:
+//   k_decompress_pair (compressed input only) -> k_verify_hash -> k_verify_ec -> k_verify_exact
+#include "kernels.h"
+
+using namespace bjj;
+
+// resident CTAs per SM the compiler must make room for (register cap = 65536 / (128 * MINB)); the carry
+// chains are dependent instruction streams, so the fma pipe needs >= 3-4 warps per SMSP to stay busy
+#ifndef BJJ_VERIFY_HASH_MINB
+#define BJJ_VERIFY_HASH_MINB 4
+#endif
+#ifndef BJJ_VERIFY_EC_MINB
+#define BJJ_VERIFY_EC_MINB 2
+#endif
+
+__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_pair(size_t n, const uint8_t* sig64, const uint8_t* pk32,
+                                                               uint8_t* r8x, uint8_t* r8y, uint8_t* ax, uint8_t* ay,
+                                                               uint8_t* status) {
+    BJJ_LANE_LOOP(n) lane_decompress_pair(sig64, pk32, r8x, r8y, ax, ay, status, i);
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_HASH_MINB) k_verify_hash(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+                                                           const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
+                                                           const uint8_t* skip, uint8_t* hm, uint8_t* ok, int gate,
+                                                           ExactQueue q, uint32_t* gflags) {
+    BJJ_FLAGS_BEGIN
+    BJJ_LANE_LOOP(n) lane_verify_hash(r8x, r8y, ax, ay, msg, skip, hm, ok, i, gate != 0, q, flags);
+    BJJ_FLAGS_END(gflags)
+}
+
+__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_EC_MINB) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+                                                         const uint8_t* s_base, size_t s_stride, size_t s_off,
+                                                         const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
+                                                         uint8_t* ok, U128* table, const CombEntry* comb) {
+    const LaneTable tbl = thread_table(table);
+    BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, i, tbl, comb);
+}
+
+// exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queue of k_verify_hash)
+__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
+                                                                  const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
+                                                                  uint8_t* ok, ExactQueue q, const CombEntry* comb) {
+    BJJ_QUEUE_LOOP(q) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, q.list[j], comb);
+}
+
+namespace bjjk {
+
+static int occ(const void* k, int block) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm;
+}
+int verify_hash_blocks_per_sm() { return occ((const void*)k_verify_hash, BJJ_BLOCK); }
+int verify_ec_blocks_per_sm() { return occ((const void*)k_verify_ec, BJJ_BLOCK); }
+int decompress_pair_blocks_per_sm() { return occ((const void*)k_decompress_pair, BJJ_BLOCK); }
+
+void decompress_pair(int grid, cudaStream_t st, size_t n, const uint8_t* sig64, const uint8_t* pk32, uint8_t* r8x,
+                     uint8_t* r8y, uint8_t* ax, uint8_t* ay, uint8_t* status) {
+    k_decompress_pair<<<grid, BJJ_BLOCK, 0, st>>>(n, sig64, pk32, r8x, r8y, ax, ay, status);
+}
+void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
+                 const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
+                 ExactQueue q, uint32_t* gflags) {
+    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, skip, hm, ok, gate ? 1 : 0, q, gflags);
+}
+void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
+               size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
+               U128* table, const CombEntry* comb) {
+    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, table, comb);
+}
+void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
+                  const uint8_t* ay, const uint8_t* msg, uint8_t* ok, ExactQueue q, const CombEntry* comb) {
+    k_verify_exact<<<grid, BJJ_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, msg, ok, q, comb);
+}
+
+}  // namespace bjjk

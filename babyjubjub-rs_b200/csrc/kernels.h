@@ -1,0 +1,64 @@
+// Host-callable launch wrappers of the heavy kernels.  Each heavy kernel lives in its own translation
+// unit (k_*.cu) so that the library builds in parallel; bjj_cuda.cu holds the light kernels, the
+// context and the C ABI.  A wrapper does exactly one <<<...>>> launch on the given stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lanes.cuh"
+
+#define BJJ_BLOCK 128
+#define BJJ_EXACT_BLOCK 64
+
+#define BJJ_LANE_LOOP(n) \
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+#define BJJ_QUEUE_LOOP(q) \
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *(q).count; j < cnt; j += gridDim.x * blockDim.x)
+#define BJJ_FLAGS_BEGIN uint32_t flags = 0;
+#define BJJ_FLAGS_END(p) \
+    if (flags) atomicOr(p, flags);
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ bjj::LaneTable thread_table(bjj::U128* base) {
+    bjj::LaneTable t;
+    t.base = base;
+    t.stride = (size_t)gridDim.x * blockDim.x;
+    t.slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    return t;
+}
+#endif
+
+struct PoseidonIn {
+    const uint8_t* p[8];
+};
+
+namespace bjjk {
+
+// resident CTAs per SM of the kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor), >= 1
+int verify_hash_blocks_per_sm();
+int verify_ec_blocks_per_sm();
+int decompress_pair_blocks_per_sm();
+int mul_scalar_blocks_per_sm();
+int sign_blocks_per_sm();
+int poseidon_blocks_per_sm(int t);
+
+void decompress_pair(int grid, cudaStream_t st, size_t n, const uint8_t* sig64, const uint8_t* pk32, uint8_t* r8x,
+                     uint8_t* r8y, uint8_t* ax, uint8_t* ay, uint8_t* status);
+void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
+                 const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
+                 bjj::ExactQueue q, uint32_t* gflags);
+void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
+               size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
+               bjj::U128* table, const bjj::CombEntry* comb);
+void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
+                  const uint8_t* ay, const uint8_t* msg, uint8_t* ok, bjj::ExactQueue q, const bjj::CombEntry* comb);
+void mul_scalar(int grid, cudaStream_t st, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
+                bjj::ProjScratch scr, bjj::U128* table, bjj::ExactQueue q, uint32_t* gflags);
+void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx,
+                      uint8_t* ry, bjj::ExactQueue q);
+void sign(int grid, cudaStream_t st, size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* r8x, uint8_t* r8y,
+          uint8_t* s32, uint8_t* status, const bjj::CombEntry* comb);
+void poseidon(int t, int grid, cudaStream_t st, size_t n, PoseidonIn in, uint8_t* out, uint32_t* gflags);
+
+}  // namespace bjjk

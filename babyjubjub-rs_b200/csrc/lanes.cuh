@@ -224,6 +224,72 @@ BJJ_HD void store_ext_affine(uint8_t* rx, uint8_t* ry, size_t i, const PointExt&
     store_fr(ry, i, a.y);
 }
 
+// Batched affine conversion (replaces one Fr::inverse per point, src/lib.rs:78, by Montgomery's trick):
+// the point kernels park (X/sqrt(-a) : Y : Z) in scratch as raw Montgomery limbs; a second kernel gives
+// every thread the lanes t, t+T, t+2T, .. and spends ONE Fermat inversion per thread:
+//   forward:  p_i = p_(i-T) * z_i (stored);   inv = 1 / p_last;
+//   backward: 1/z_i = inv * p_(i-T);  inv *= z_i;   x_i = X_i / z_i,  y_i = Y_i / z_i.
+// Z == 0 keeps the reference rule of PointProjective::affine (src/lib.rs:71-76): the lane yields (0, 0)
+// and is left out of the product.  Off-curve lanes of mul_scalar park Z = 0 and are overwritten by the
+// exact-lane kernel afterwards.
+struct ProjScratch {
+    uint8_t* x;
+    uint8_t* y;
+    uint8_t* z;
+    uint8_t* p;    // running products
+};
+
+BJJ_HD void store_ext_scratch(const ProjScratch& s, size_t i, const PointExt& p) {
+    PointProj pj;
+    ext_to_proj(pj, p);
+    store_u256(s.x, i, pj.x.v);
+    store_u256(s.y, i, pj.y.v);
+    store_u256(s.z, i, pj.z.v);
+}
+BJJ_HD void store_zero_scratch(const ProjScratch& s, size_t i) {
+    Fr z;
+    fr_zero(z);
+    store_u256(s.x, i, z.v);
+    store_u256(s.y, i, z.v);
+    store_u256(s.z, i, z.v);
+}
+
+BJJ_HD void batch_affine_strided(const ProjScratch& s, uint8_t* rx, uint8_t* ry, size_t n, size_t t, size_t T) {
+    if (t >= n) return;
+    const Fr one = fr_const(BJJ_ONE_M);
+    Fr acc = one, z;
+    size_t last = t;
+#pragma unroll 1
+    for (size_t i = t; i < n; i += T) {
+        load_u256(z.v, s.z, i);
+        if (!fr_is_zero(z)) fr_mul(acc, acc, z);
+        store_u256(s.p, i, acc.v);
+        last = i;
+    }
+    Fr inv;
+    fr_inv(inv, acc);
+#pragma unroll 1
+    for (size_t i = last;; i -= T) {
+        Fr prev = one, zi, x, y;
+        if (i >= t + T) load_u256(prev.v, s.p, i - T);
+        load_u256(z.v, s.z, i);
+        const bool zero = fr_is_zero(z);
+        fr_mul(zi, inv, prev);
+        if (!zero) fr_mul(inv, inv, z);
+        load_u256(x.v, s.x, i);
+        load_u256(y.v, s.y, i);
+        fr_mul(x, x, zi);
+        fr_mul(y, y, zi);
+        if (zero) {
+            fr_zero(x);
+            fr_zero(y);
+        }
+        store_fr(rx, i, x);
+        store_fr(ry, i, y);
+        if (i < t + T) break;
+    }
+}
+
 // ---- lane bodies --------------------------------------------------------------------------------------
 
 // test hook for Fr (reference Fr ops: mul_assign / square / add_assign / sub_assign / inverse)
@@ -343,12 +409,13 @@ BJJ_HD void exact_push(const ExactQueue& q, size_t i) {
 }
 
 // Point::mul_scalar (src/lib.rs:149-164): on-curve gate -> fast ladder, else queued for the exact lane.
-BJJ_HD void lane_mul_scalar(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, uint8_t* rx,
-                            uint8_t* ry, size_t i, const LaneTable& tbl, const ExactQueue& q, uint32_t& flags) {
+BJJ_HD void lane_mul_scalar(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, const ProjScratch& scr,
+                            size_t i, const LaneTable& tbl, const ExactQueue& q, uint32_t& flags) {
     PointAff p;
     load_fr(p.x, px, i, flags);
     load_fr(p.y, py, i, flags);
     if (!on_curve(p)) {
+        store_zero_scratch(scr, i);      // Z = 0: skipped by the batched affine pass, written by the exact kernel
         exact_push(q, i);
         return;
     }
@@ -357,7 +424,7 @@ BJJ_HD void lane_mul_scalar(const uint8_t* px, const uint8_t* py, const uint8_t*
     PointExt e, acc;
     ext_from_affine(e, p);
     var_base_mul(acc, e, n, tbl);
-    store_ext_affine(rx, ry, i, acc);
+    store_ext_scratch(scr, i, acc);
 }
 
 // exact lane of mul_scalar: lane index taken from the queue
@@ -375,22 +442,22 @@ BJJ_HD void lane_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const ui
 }
 
 // B8.mul_scalar(k) for a raw 256-bit scalar (src/lib.rs:305, :329, :405)
-BJJ_HD void lane_fixed_base(const uint8_t* scalar, uint8_t* rx, uint8_t* ry, size_t i, const CombEntry* comb) {
+BJJ_HD void lane_fixed_base(const uint8_t* scalar, const ProjScratch& scr, size_t i, const CombEntry* comb) {
     uint32_t k[8];
     load_u256(k, scalar, i);
     PointExt acc;
     fixed_base_comb(acc, comb, k);
-    store_ext_affine(rx, ry, i, acc);
+    store_ext_scratch(scr, i, acc);
 }
 
 // PrivateKey::public (src/lib.rs:304-306) = B8 * scalar_key(key)
-BJJ_HD void lane_public(const uint8_t* key, uint8_t* rx, uint8_t* ry, size_t i, const CombEntry* comb) {
+BJJ_HD void lane_public(const uint8_t* key, const ProjScratch& scr, size_t i, const CombEntry* comb) {
     uint32_t kw[8], k[8];
     load_u256(kw, key, i);
     scalar_key_from_key(k, kw);
     PointExt acc;
     fixed_base_comb(acc, comb, k);
-    store_ext_affine(rx, ry, i, acc);
+    store_ext_scratch(scr, i, acc);
 }
 
 // PrivateKey::scalar_key (src/lib.rs:284-302) test hook
@@ -640,10 +707,8 @@ BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& m
 }
 
 // requires A and R8 ON the curve
-BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m,
+BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& hm,
                             const LaneTable& tbl, const CombEntry* comb) {
-    Fr hm;
-    verify_hm(hm, r8, a, msg_m);
     PointExt pa, acc;
     ext_from_affine(pa, a);
     ext_dbl<false>(pa, pa);
@@ -689,19 +754,47 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAf
 }
 
 // any A / R8 (also off the curve): src/lib.rs:395-412 operation for operation
-BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m) {
+// Exact lane of verify: taken when R8 or A is not on the curve.  Every step whose inputs ARE curve
+// points still yields the group element the reference computes (complete addition law), so only the
+// off-curve parts replay the reference sequence:
+//   l  = B8.mul_scalar(S)          B8 is on the curve            -> comb (same affine point)
+//   kA = A.mul_scalar(8*hm)        A on the curve  -> hm * (8A) by a table-free binary ladder
+//                                  A off the curve -> literal LSB-first double-and-add (src/lib.rs:149-164)
+//   r  = R8 + kA, affine           literal add-2008-bbjlp + affine (Z == 0 -> (0,0)), src/lib.rs:407-411
+BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m,
+                             const CombEntry* comb) {
     Fr hm;
     verify_hm(hm, r8, a, msg_m);
-    PointAff b8, l, ka, ra;
-    b8.x = fr_const(BJJ_B8X_M);
-    b8.y = fr_const(BJJ_B8Y_M);
-    mul_scalar_exact(l, b8, s, 8);
-    uint32_t k9[9];
-    k9[0] = hm.v[0] << 3;
+    PointAff l, ka, ra;
+    PointExt acc;
+    PointProj pj;
+    fixed_base_comb(acc, comb, s);
+    ext_to_proj(pj, acc);
+    proj_affine(l, pj);
+    if (on_curve(a)) {
+        PointExt p8;
+        ext_from_affine(p8, a);
+        ext_dbl<false>(p8, p8);
+        ext_dbl<false>(p8, p8);
+        ext_dbl<true>(p8, p8);
+        Niels n8;
+        niels_from_ext(n8, p8);
+        ext_identity(acc);
+#pragma unroll 1
+        for (int i = 253; i >= 0; i--) {      // hm < Q < 2^254
+            ext_dbl<true>(acc, acc);
+            if ((hm.v[i >> 5] >> (i & 31)) & 1) ext_add_niels<false>(acc, acc, n8);
+        }
+        ext_to_proj(pj, acc);
+        proj_affine(ka, pj);
+    } else {
+        uint32_t k9[9];
+        k9[0] = hm.v[0] << 3;
 #pragma unroll
-    for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
-    k9[8] = hm.v[7] >> 29;
-    mul_scalar_exact(ka, a, k9, 9);
+        for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
+        k9[8] = hm.v[7] >> 29;
+        mul_scalar_exact(ka, a, k9, 9);
+    }
     PointProj pr, pk, sum;
     pr.x = r8.x;
     pr.y = r8.y;
@@ -733,26 +826,64 @@ BJJ_HD bool verify_load(PointAff& r8, uint32_t* s, PointAff& a, Fr& mm, const ui
     return true;
 }
 
-BJJ_HD void lane_verify(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
-                        const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i, const LaneTable& tbl,
-                        const CombEntry* comb, const ExactQueue& q, uint32_t& flags) {
-    uint32_t s[8];
-    PointAff r8, a;
-    Fr mm;
-    if (!verify_load(r8, s, a, mm, r8x, r8y, s32, ax, ay, msg32, i, flags)) {
+// verify runs as a short pipeline of kernels so that no kernel carries another phase's registers or code:
+//   phase 1 (lane_verify_hash): msg range check, on-curve gate (exact lanes are queued), hm = Poseidon(..)
+//                               -> hm[i] (canonical integer), ok[i] = BJJ_OK_PENDING
+//   phase 2 (lane_verify_ec):   Straus pass for the pending lanes -> ok[i] in {0, 1}
+//   phase 3 (lane_verify_exact, other kernel): the queued off-curve lanes.
+// `skip` (may be null): lanes whose decompression failed (verify_compressed) are rejected up front.
+#define BJJ_OK_PENDING 2
+BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
+                             const uint8_t* msg32, const uint8_t* skip, uint8_t* hm_out, uint8_t* ok, size_t i,
+                             bool gate, const ExactQueue& q, uint32_t& flags) {
+    if (skip && skip[i]) {
         ok[i] = 0;
         return;
     }
-    if (!(on_curve(a) && on_curve(r8))) {
+    uint32_t msg[8];
+    load_u256(msg, msg32, i);
+    const uint32_t qq[8] = BJJ_LIMBS8(BJJ_Q);
+    if (u256_lt(qq, msg)) {     // msg > Q -> false; msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
+        ok[i] = 0;
+        return;
+    }
+    PointAff r8, a;
+    load_fr(r8.x, r8x, i, flags);
+    load_fr(r8.y, r8y, i, flags);
+    load_fr(a.x, ax, i, flags);
+    load_fr(a.y, ay, i, flags);
+    if (gate && !(on_curve(a) && on_curve(r8))) {
         ok[i] = 0;
         exact_push(q, i);
         return;
     }
-    ok[i] = (uint8_t)verify_fast(r8, s, a, mm, tbl, comb);
+    Fr mraw, mm, hm;
+    fr_set(mraw, msg);
+    fr_to_mont(mm, mraw);
+    verify_hm(hm, r8, a, mm);
+    store_u256(hm_out, i, hm.v);
+    ok[i] = BJJ_OK_PENDING;
+}
+
+// S of lane i sits at 32-byte element index i * s_stride + s_off (1, 0 for a plain S array; 2, 1 inside sig64)
+BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base, size_t s_stride,
+                           size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm_in, uint8_t* ok,
+                           size_t i, const LaneTable& tbl, const CombEntry* comb) {
+    if (ok[i] != BJJ_OK_PENDING) return;
+    uint32_t s[8], flags = 0;
+    PointAff r8, a;
+    Fr hm;
+    load_u256(s, s_base, i * s_stride + s_off);
+    load_u256(hm.v, hm_in, i);
+    load_fr(r8.x, r8x, i, flags);
+    load_fr(r8.y, r8y, i, flags);
+    load_fr(a.x, ax, i, flags);
+    load_fr(a.y, ay, i, flags);
+    ok[i] = (uint8_t)verify_fast(r8, s, a, hm, tbl, comb);
 }
 
 BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
-                              const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i) {
+                              const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i, const CombEntry* comb) {
     uint32_t s[8], flags = 0;
     PointAff r8, a;
     Fr mm;
@@ -760,37 +891,30 @@ BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint
         ok[i] = 0;
         return;
     }
-    ok[i] = (uint8_t)verify_exact(r8, s, a, mm);
+    ok[i] = (uint8_t)verify_exact(r8, s, a, mm, comb);
 }
 
-// decompress_signature + decompress(pk) + verify (src/lib.rs:260-268, 192-224, 395-412):
-// sig64 = compress(R8) || S_le32, pk32 = compress(A).  status = first decompression error (R8 first,
-// then A), ok = 0 whenever status != 0.  Decompressed points are on the curve by construction, so this
-// pipeline never needs the exact lane.
-BJJ_HD void lane_verify_compressed(const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msg32, uint8_t* ok,
-                                   uint8_t* status, size_t i, const LaneTable& tbl, const CombEntry* comb) {
-    uint32_t rb[8], s[8], ab[8], msg[8];
+// decompress_signature + decompress(pk) (src/lib.rs:260-268, 192-224): phase 0 of verify_compressed.
+// sig64 = compress(R8) || S_le32, pk32 = compress(A).  status = first decompression error (R8 first, then
+// A); the decompressed coordinates go to scratch as canonical bytes and the verify phases run on them
+// with the gate off (decompressed points are on the curve by construction).
+BJJ_HD void lane_decompress_pair(const uint8_t* sig64, const uint8_t* pk32, uint8_t* r8x, uint8_t* r8y, uint8_t* ax,
+                                 uint8_t* ay, uint8_t* status, size_t i) {
+    uint32_t rb[8], ab[8];
     load_u256(rb, sig64, 2 * i);
-    load_u256(s, sig64, 2 * i + 1);
     load_u256(ab, pk32, i);
-    load_u256(msg, msg32, i);
     PointAff r8, a;
+    fr_zero(r8.x);
+    fr_zero(r8.y);
+    fr_zero(a.x);
+    fr_zero(a.y);
     uint32_t st = decompress_core(r8.x, r8.y, rb);
     if (st == BJJ_ST_OK) st = decompress_core(a.x, a.y, ab);
     status[i] = (uint8_t)st;
-    if (st != BJJ_ST_OK) {
-        ok[i] = 0;
-        return;
-    }
-    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
-    if (u256_lt(q, msg)) {
-        ok[i] = 0;
-        return;
-    }
-    Fr mraw, mm;
-    fr_set(mraw, msg);
-    fr_to_mont(mm, mraw);
-    ok[i] = (uint8_t)verify_fast(r8, s, a, mm, tbl, comb);
+    store_fr(r8x, i, r8.x);
+    store_fr(r8y, i, r8.y);
+    store_fr(ax, i, a.x);
+    store_fr(ay, i, a.y);
 }
 
 }  // namespace bjj

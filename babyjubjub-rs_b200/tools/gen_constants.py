@@ -105,6 +105,86 @@ def poseidon_tables(t):
     return rc, mds
 
 
+# ---- optimised schedule: sparse partial-round matrices ----------------------------------------------
+# The dense permutation  x <- M * sbox(x + c_r)  is algebraically rewritten (exact field arithmetic, so
+# the hash is bit-identical):  in a partial round only lane 0 goes through x^5, so the block-diagonal
+# part A' = diag(1, A_hat) of a round matrix A = S * A' commutes with the S-box layer and is pushed
+# into the PREVIOUS round.  Working backwards from the last partial round leaves, per partial round, a
+# sparse matrix S_r = [[a00, what], [v, I]] (2t-1 products instead of t^2) and ONE scalar constant k_r;
+# the leftovers are a dense matrix P = A'_1 * M used by full round 3 and one vector added before the
+# first partial round.  (Technique: Poseidon paper, appendix "optimised implementation".)
+def _matmul(a, b):
+    return [[sum(a[i][k] * b[k][j] for k in range(len(b))) % Q for j in range(len(b[0]))] for i in range(len(a))]
+
+
+def _matvec(a, v):
+    return [sum(x * y for x, y in zip(row, v)) % Q for row in a]
+
+
+def _inverse(a):
+    n = len(a)
+    m = [row[:] + [int(i == j) for j in range(n)] for i, row in enumerate(a)]
+    for c in range(n):
+        p = next(r for r in range(c, n) if m[r][c] % Q)
+        m[c], m[p] = m[p], m[c]
+        iv = inv(m[c][c])
+        m[c] = [x * iv % Q for x in m[c]]
+        for r in range(n):
+            if r != c and m[r][c]:
+                f = m[r][c]
+                m[r] = [(x - f * y) % Q for x, y in zip(m[r], m[c])]
+    return [row[n:] for row in m]
+
+
+def poseidon_optimized(t):
+    rc, mds = poseidon_tables(t)
+    rp = R_P[t]
+    rounds = [rc[r * t:(r + 1) * t] for r in range(R_F + rp)]
+    part = rounds[R_F // 2:R_F // 2 + rp]
+    sparse = [None] * (rp + 1)
+    chat = [None] * (rp + 2)
+    a = [row[:] for row in mds]
+    for r in range(rp, 0, -1):
+        ahat = [row[1:] for row in a[1:]]
+        ainv = _inverse(ahat)
+        wrow = a[0][1:]
+        what = [sum(wrow[k] * ainv[k][j] for k in range(t - 1)) % Q for j in range(t - 1)]
+        sparse[r] = (a[0][0], what, [a[i][0] for i in range(1, t)])
+        aprime = [[1] + [0] * (t - 1)] + [[0] + ahat[i] for i in range(t - 1)]
+        chat[r] = _matvec(aprime, part[r - 1])
+        a = _matmul(aprime, mds)
+    # constants: lanes 1.. are pushed back to one vector; lane 0 keeps one scalar per round
+    d = [0] * (t - 1)
+    k = [0] * (rp + 2)
+    for r in range(rp, 0, -1):
+        if r + 1 <= rp:
+            k[r + 1] = (chat[r + 1][0] - sum(x * y for x, y in zip(sparse[r][1], d))) % Q
+        d = [(chat[r][1 + i] + d[i]) % Q for i in range(t - 1)]
+    pre = [chat[1][0]] + d
+    partial = [[k[r] if r > 1 else 0, sparse[r][0]] + sparse[r][1] + sparse[r][2] for r in range(1, rp + 1)]
+    return {"full_rc": rounds[:R_F // 2] + rounds[R_F // 2 + rp:], "pre": pre, "partial": partial, "M": mds, "P": a}
+
+
+def poseidon_optimized_eval(inputs):
+    """reference evaluation of the optimised schedule (used by tests to pin it on the dense oracle)"""
+    t = len(inputs) + 1
+    o = poseidon_optimized(t)
+    x = [0] + [v % Q for v in inputs]
+    for r in range(R_F // 2):
+        x = [pow((p + c) % Q, 5, Q) for p, c in zip(x, o["full_rc"][r])]
+        x = _matvec(o["P"] if r == R_F // 2 - 1 else o["M"], x)
+    x = [(p + c) % Q for p, c in zip(x, o["pre"])]
+    for row in o["partial"]:
+        x0 = pow((x[0] + row[0]) % Q, 5, Q)
+        what, v = row[2:2 + t - 1], row[2 + t - 1:]
+        n0 = (row[1] * x0 + sum(p * q for p, q in zip(what, x[1:]))) % Q
+        x = [n0] + [(x[i] + v[i - 1] * x0) % Q for i in range(1, t)]
+    for r in range(R_F // 2, R_F):
+        x = [pow((p + c) % Q, 5, Q) for p, c in zip(x, o["full_rc"][r])]
+        x = _matvec(o["M"], x)
+    return x[0]
+
+
 # ---- emit ---------------------------------------------------------------------------------------
 def limbs(x):
     assert 0 <= x < (1 << 256)
@@ -194,18 +274,22 @@ def emit(out):
     w("};\n\n")
 
     for t in range(2, 10):
-        rc, mds = poseidon_tables(t)
+        o = poseidon_optimized(t)
         w("#define BJJ_POSEIDON_RP_%d %d\n" % (t, R_P[t]))
         space = "BJJ_CONST" if t == 6 else "BJJ_TABLE"   # t=6 (verify) sits in the constant bank
-        w("%s uint32_t BJJ_POSEIDON_C%d[%d][8] = {\n" % (space, t, len(rc)))
-        for c in rc:
-            w(" %s,\n" % fmt(mont(c)))
-        w("};\n")
-        w("%s uint32_t BJJ_POSEIDON_M%d[%d][8] = {   // row-major M[i][j]\n" % (space, t, t * t))
-        for i in range(t):
-            for j in range(t):
-                w(" %s,\n" % fmt(mont(mds[i][j])))
-        w("};\n\n")
+
+        def table(name, elems, note=""):
+            w("%s uint32_t BJJ_POSEIDON_%s%d[%d][8] = {%s\n" % (space, name, t, len(elems), ("   // " + note) if note else ""))
+            for e in elems:
+                w(" %s,\n" % fmt(mont(e)))
+            w("};\n")
+        table("FC", [c for r in o["full_rc"] for c in r], "round constants of the 8 full rounds, [round][lane]")
+        table("PRE", o["pre"], "vector added once before the partial rounds")
+        table("PR", [e for r in o["partial"] for e in r],
+              "per partial round: k, a00, what[1..t-1], v[1..t-1]  (2t elements)")
+        table("M", [o["M"][i][j] for i in range(t) for j in range(t)], "row-major MDS")
+        table("P", [o["P"][i][j] for i in range(t) for j in range(t)], "row-major matrix of full round 3 (= A'_1 * M)")
+        w("\n")
 
 
 def main():

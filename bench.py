@@ -36,23 +36,28 @@ SUBORDER = 218882428718392752222464057452572750886145117772685380736017252875875
 METRIC = "eddsa_poseidon_verifies_per_sec"
 UNIT = "verifies/s"
 
-# Algorithmic work per unit, in limb-MACs (one 32x32->64 multiply-accumulate = one IMAD.WIDE.U32 on
-# sm_100a; 1 field multiplication = 136).  Derivations: DESIGN.md "Kernels and rooflines".
-FMUL = 136
+# Algorithmic work per unit, in limb-MACs (one 32x32->64 multiply-accumulate = one IMAD.WIDE.U32 on sm_100a).
+# fmul = fsqr = 128 (8x8 products + 8x8 Montgomery reduction; the 8 m_i IMADs are not counted), a Montgomery dot
+# product of N terms = 64 N + 64.  Counts are for the algorithms actually built; derivations in DESIGN.md section 6.
+FMUL = 128
 ALGO_FMUL = {
-    # Straus pass: 64 windows x (3 dbl x 7 + 1 dbl x 8 + add 8) + 33 mixed adds x 7 + table 64 + 3 dbl 23
-    #              + gates 10 + compare 3 + maps 4 = 2703; Poseidon t=6 dense with fused row reductions:
-    #              68 x 6 rows x (6*64+72) MAC + (8*6+60) x 3 fmul  -> counted in MACs below
-    "verify_ec": 2703,
-    "fixed_base": 33 * 7 + 2 + 270,       # comb + map + per-lane Fermat inverse (254 S + 16 M window-less)
-    "mul_scalar": 64 * 37 + 64 + 6 + 2 + 270,
+    # gates 10 + Montgomery conversions 10 + map 2 + 8A 22 + table 64 + first adds 15
+    # + 32 x (2 x (3 x 7 + 8) + 7 + 8 + 6) Straus windows + projective compare 3
+    "verify_ec": 10 + 10 + 2 + 22 + 64 + 15 + 32 * (2 * 29 + 21) + 3,
+    "fixed_base": 33 * 7 + 1 + 5 + 2 + 12,            # comb + map + batched inversion share
+    "mul_scalar": 2 + 5 + 2 + 64 + 7 + 64 * 36 + 20,  # gate, table, 64 windows x (4 dbl + add), batched inversion share
 }
-POSEIDON6_MAC = 68 * 6 * (6 * 64 + 72) + (8 * 6 + 60) * 3 * FMUL
+# Poseidon t = 6, sparse schedule: 8 full rounds x (6 x^5 + 6 dot6) + 60 partial x (x^5 + dot6 + 5 fmul)
+POSEIDON6_MAC = 8 * (6 * 3 * FMUL + 6 * (6 * 64 + 64)) + 60 * (3 * FMUL + (6 * 64 + 64) + 5 * FMUL)
 ALGO_MAC = {
     "verify": ALGO_FMUL["verify_ec"] * FMUL + POSEIDON6_MAC,
     "fixed_base": ALGO_FMUL["fixed_base"] * FMUL,
     "mul_scalar": ALGO_FMUL["mul_scalar"] * FMUL,
 }
+# Measured on B200 (profiles/r1_pipe_probe.jsonl): IMAD.WIDE.U32 issues at 32 lanes/clk/SM -- half the 32-bit IMAD
+# rate that SURVEY.md section 8d's model (64 lanes/clk/SM) assumes.
+WIDE_MAC_LANES_PER_CLK_SM = 32
+MODEL_LANES_PER_CLK_SM = 64
 
 
 def measured_peaks():
@@ -362,17 +367,20 @@ def run_ours(args, rank, local_rank, world):
     peaks, peak_kind = measured_peaks()
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    imad_peak = sms * 64 * sm_max * 1e6 / 1e12            # T thread-IMAD/s at max clock
+    mac_peak = sms * WIDE_MAC_LANES_PER_CLK_SM * sm_max * 1e6 / 1e12      # T limb-MAC/s, measured IMAD.WIDE rate
+    model_peak = sms * MODEL_LANES_PER_CLK_SM * sm_max * 1e6 / 1e12        # SURVEY model (32-bit IMAD rate)
     per_gpu = value / world
     achieved = per_gpu * ALGO_MAC["verify"] / 1e12
     roofline = {
-        "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD/s", "frac": achieved / imad_peak,
-        "peak_formula": "%d SMs x 64 lanes x %.0f MHz (fma pipe, 16 lanes/SMSP); model, see profiles/ for the measured IMAD rate" % (sms, sm_max),
+        "bound": "imad", "achieved": achieved, "peak": mac_peak, "unit": "T limb-MAC/s", "frac": achieved / mac_peak,
+        "peak_kind": "measured: %d SMs x %d IMAD.WIDE lanes/clk x %.0f MHz (profiles/r1_pipe_probe.jsonl)" % (sms, WIDE_MAC_LANES_PER_CLK_SM, sm_max),
+        "frac_of_survey_model": achieved / model_peak,
+        "survey_model_peak": model_peak,
         "algorithmic_mac_per_verify": ALGO_MAC["verify"],
-        "frac_at_observed_clock": (achieved / (sms * 64 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
+        "frac_at_observed_clock": (achieved / (sms * WIDE_MAC_LANES_PER_CLK_SM * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
         "traffic": None,
         "hbm": {"achieved_gbs": per_gpu * 193 / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind,
-                "note": "193 B per verify (6 x 32 B in, 1 B out) + per-thread window table via L2"},
+                "note": "193 B per verify (6 x 32 B in, 1 B out); secondary counter, this path is not HBM-bound"},
     }
 
     secondary = []
@@ -391,7 +399,7 @@ def run_ours(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 (8x32-bit Montgomery limbs, IMAD.WIDE.U32)", "data": "synthetic",
+        "dtype": "u32", "data": "synthetic",
         "config": {"workload": "verify_batch: 2^%d EdDSA-Poseidon signatures per GPU (config 4: 2^24 over 8 GPUs), 10%% corrupted in 8 classes"
                                % args.log2_lanes,
                    "signatures_per_gpu": n, "l2": "inputs larger than L2 (%.0f MB per step)" % (n * 192 / 1e6),
@@ -437,7 +445,7 @@ def run_secondaries(args, eng, torch, dev, stream, common):
 
     peaks, _ = measured_peaks()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    imad_peak = sms * 64 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    imad_peak = sms * WIDE_MAC_LANES_PER_CLK_SM * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
 
     # config 2: PrivateKey::public over 2^20 random keys
     n = 1 << 20

@@ -26,6 +26,22 @@ static ExactQueue exact_queue(size_t n) {
     return q;
 }
 
+static std::vector<uint8_t> g_scr;
+static ProjScratch proj_scratch(size_t n) {
+    g_scr.assign(4 * 32 * (n + 1), 0);
+    ProjScratch s;
+    s.x = g_scr.data();
+    s.y = s.x + 32 * n;
+    s.z = s.y + 32 * n;
+    s.p = s.z + 32 * n;
+    return s;
+}
+// the batched affine pass with T "threads" (T = 3 exercises several strides and ragged tails)
+static void batch_affine(const ProjScratch& s, uint8_t* rx, uint8_t* ry, size_t n) {
+    const size_t T = 3;
+    for (size_t t = 0; t < T; t++) batch_affine_strided(s, rx, ry, n, t, T);
+}
+
 static LaneTable lane_table() {
     LaneTable t;
     t.base = g_table.data();
@@ -84,19 +100,25 @@ uint32_t emu_affine(size_t n, const uint8_t* px, const uint8_t* py, const uint8_
 uint32_t emu_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx, uint8_t* ry) {
     uint32_t flags = 0;
     ExactQueue q = exact_queue(n);
-    for (size_t i = 0; i < n; i++) lane_mul_scalar(px, py, k, rx, ry, i, lane_table(), q, flags);
+    ProjScratch scr = proj_scratch(n);
+    for (size_t i = 0; i < n; i++) lane_mul_scalar(px, py, k, scr, i, lane_table(), q, flags);
+    batch_affine(scr, rx, ry, n);
     for (uint32_t j = 0; j < g_count; j++) lane_mul_scalar_exact(px, py, k, rx, ry, g_list[j]);
     return flags;
 }
 
 void emu_fixed_base(size_t n, const uint8_t* k, uint8_t* rx, uint8_t* ry) {
     emu_init();
-    for (size_t i = 0; i < n; i++) lane_fixed_base(k, rx, ry, i, g_comb);
+    ProjScratch scr = proj_scratch(n);
+    for (size_t i = 0; i < n; i++) lane_fixed_base(k, scr, i, g_comb);
+    batch_affine(scr, rx, ry, n);
 }
 
 void emu_public(size_t n, const uint8_t* key, uint8_t* rx, uint8_t* ry) {
     emu_init();
-    for (size_t i = 0; i < n; i++) lane_public(key, rx, ry, i, g_comb);
+    ProjScratch scr = proj_scratch(n);
+    for (size_t i = 0; i < n; i++) lane_public(key, scr, i, g_comb);
+    batch_affine(scr, rx, ry, n);
 }
 
 void emu_scalar_key(size_t n, const uint8_t* key, uint8_t* out) {
@@ -141,15 +163,23 @@ uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint
     emu_init();
     uint32_t flags = 0;
     ExactQueue q = exact_queue(n);
-    for (size_t i = 0; i < n; i++) lane_verify(r8x, r8y, s, ax, ay, msg, ok, i, lane_table(), g_comb, q, flags);
-    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, g_list[j]);
+    std::vector<uint8_t> hm(32 * (n + 1));
+    for (size_t i = 0; i < n; i++) lane_verify_hash(r8x, r8y, ax, ay, msg, nullptr, hm.data(), ok, i, true, q, flags);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, s, 1, 0, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
+    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, g_list[j], g_comb);
     return flags;
 }
 
 void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msg, uint8_t* ok,
                            uint8_t* status) {
     emu_init();
-    for (size_t i = 0; i < n; i++) lane_verify_compressed(sig64, pk32, msg, ok, status, i, lane_table(), g_comb);
+    std::vector<uint8_t> d(4 * 32 * (n + 1)), hm(32 * (n + 1));
+    uint8_t *dx = d.data(), *dy = dx + 32 * n, *ax = dy + 32 * n, *ay = ax + 32 * n;
+    uint32_t flags = 0;
+    ExactQueue q = exact_queue(n);
+    for (size_t i = 0; i < n; i++) lane_decompress_pair(sig64, pk32, dx, dy, ax, ay, status, i);
+    for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, flags);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, sig64, 2, 1, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
 }
 
 }  // extern "C"

@@ -45,3 +45,13 @@ def test_emitted_constants_decode():
     assert const("INV_SQRT_NEG_A_M") * rinv % Q * s % Q == 1
     assert const("SUBORDER") == O.SUBORDER and const("ORDER") == O.ORDER
     assert const("TWO_DP_M") * rinv % Q == (-2 * O.D * pow(O.A, -1, Q)) % Q
+
+
+def test_optimized_poseidon_schedule_equals_dense():
+    """the sparse partial-round schedule baked into the GPU tables must hash like the dense oracle"""
+    import random
+    g = _gen()
+    rnd = random.Random(9)
+    for t in range(2, 10):
+        for ins in ([0] * (t - 1), list(range(1, t)), [rnd.randrange(Q) for _ in range(t - 1)]):
+            assert g.poseidon_optimized_eval(ins) == O.poseidon(ins), t
