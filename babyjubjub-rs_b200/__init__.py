@@ -23,6 +23,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import BjjError
+from .sharding import MultiGpu, max_over_ranks, shard_range  # noqa: F401
 
 Q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 ORDER = 21888242871839275222246405745257275088614511777268538073601725287587578984328
@@ -365,3 +366,24 @@ def verify_batch(pks, sigs, msgs, engine=None):
                           ints_to_le32([s.s for s in sigs]), ints_to_le32([p.x for p in pks]),
                           ints_to_le32([p.y for p in pks]), ints_to_le32(mm))
     return [bool(v) for v in ok]
+
+
+def multi_gpu(devices=None):
+    """One Engine per device (all visible devices by default); see sharding.MultiGpu.run_sharded"""
+    lib = _lib.load()
+    if devices is None:
+        devices = list(range(lib.bjj_device_count()))
+    if not devices:
+        raise RuntimeError("babyjubjub-rs_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return MultiGpu(Engine, devices)
+
+
+def verify_batch_multi(mg, r8x, r8y, s, ax, ay, msg):
+    """verify_batch sharded over every device of `mg` (contiguous slices, one host thread per device)"""
+    ins = [_as_u8(v, 32) for v in (r8x, r8y, s, ax, ay, msg)]
+    ok = np.empty(len(ins[0]), dtype=np.uint8)
+
+    def work(eng, lo, hi):
+        ok[lo:hi] = eng.verify_batch(*[v[lo:hi] for v in ins])
+    mg.run_sharded(len(ok), work)
+    return ok

@@ -273,11 +273,7 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return bjj.max_over_ranks(x, dist, dev)
 
     # ---- data: keys / msgs random on the device; signatures by the library's sign kernel -------------
     g = torch.Generator(device=dev)

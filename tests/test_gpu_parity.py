@@ -122,3 +122,14 @@ def test_large_batch_properties(gpu, oracle_c):
     b8x, b8y = pack([O.B8[0]] * 4096), pack([O.B8[1]] * 4096)
     vx, vy = gpu.eng.mul_scalar_batch(b8x, b8y, k[:4096])
     assert np.array_equal(vx, rx[:4096]) and np.array_equal(vy, ry[:4096])
+
+
+def test_multi_device_sharding(gpu, oracle_c):
+    """verify_batch sharded over every visible device (one on the test box) equals the oracle"""
+    import random
+    from common import cases_to_arrays, signature_cases
+    bjj = gpu.bjj
+    mg = bjj.multi_gpu()
+    arrs = cases_to_arrays(signature_cases(random.Random(21), 5))
+    ok = bjj.verify_batch_multi(mg, *arrs)
+    assert np.array_equal(ok, oracle_c.verify(*arrs))
