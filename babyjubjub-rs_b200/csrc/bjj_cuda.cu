@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_decompress(size_t n, const uint8_
 struct Workspace {
     U128* table;
     size_t table_slots;
-    uint32_t* exact_count;   // one device word
-    uint32_t* exact_list;
+    uint32_t* exact_count;   // two device words (one per queue)
+    uint32_t* exact_list;    // 2 x exact_cap indices
     size_t exact_cap;
     uint8_t* proj;           // 4 x 32 B per lane: X, Y, Z, running product
     size_t proj_lanes;
@@ -155,19 +155,23 @@ static int ensure_table(bjj_ctx* ctx, Workspace* ws, size_t slots) {
     return BJJ_OK;
 }
 
-// makes room for n queued lane indices and zeroes the counter on `st`
-static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, ExactQueue* q) {
-    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, sizeof(uint32_t)));
+// makes room for two queues of n lane indices each and zeroes both counters on `st`
+static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, ExactQueue* q, ExactQueue* q2 = nullptr) {
+    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, 2 * sizeof(uint32_t)));
     if (ws->exact_cap < n) {
         if (ws->exact_list) cudaFree(ws->exact_list);
         ws->exact_list = nullptr;
         ws->exact_cap = 0;
-        CU(ctx, cudaMalloc(&ws->exact_list, n * sizeof(uint32_t)));
+        CU(ctx, cudaMalloc(&ws->exact_list, 2 * n * sizeof(uint32_t)));
         ws->exact_cap = n;
     }
-    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, sizeof(uint32_t), st));
+    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, 2 * sizeof(uint32_t), st));
     q->count = ws->exact_count;
     q->list = ws->exact_list;
+    if (q2) {
+        q2->count = ws->exact_count + 1;
+        q2->list = ws->exact_list + ws->exact_cap;
+    }
     return BJJ_OK;
 }
 
@@ -177,7 +181,6 @@ static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, 
 static int ensure_proj(bjj_ctx* ctx, Workspace* ws, size_t lanes, ProjScratch* scr) {
     if (ws->proj_lanes < lanes) {
         if (ws->proj) cudaFree(ws->proj);
-    if (ws->vs) cudaFree(ws->vs);
         ws->proj = nullptr;
         ws->proj_lanes = 0;
         CU(ctx, cudaMalloc(&ws->proj, lanes * 128));
@@ -448,29 +451,50 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
         int rc = ensure_table(ctx, ws, (size_t)grid_e * BJJ_BLOCK);
         if (rc) return rc;
-        ExactQueue q;
-        rc = ensure_queue(ctx, ws, m, st, &q);
+        ExactQueue qa, qr;
+        rc = ensure_queue(ctx, ws, m, st, &qa, &qr);
         if (rc) return rc;
         uint8_t *hm, *pts;
         rc = ensure_vscratch(ctx, ws, n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &hm, &pts);
         if (rc) return rc;
         rc = ensure_aux(ctx, ws);
         if (rc) return rc;
-        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, nullptr, hm, ok + off, true, q, ctx->flags_dev);
+        // BJJ_PHASE_TIMING=1: synchronous per-phase CUDA-event timings on stderr (diagnosis only)
+        static const bool phase_timing = getenv("BJJ_PHASE_TIMING") != nullptr;
+        cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (phase_timing) {
+            for (int e = 0; e < 4; e++) cudaEventCreate(&pe[e]);
+            cudaEventRecord(pe[0], st);
+        }
+        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, nullptr, hm, ok + off, true, qa, qr, ctx->flags_dev);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        // the queue is complete: the (slow, rare) exact lanes run on the side stream, concurrently with the
-        // Straus kernel; both write disjoint ok[] lanes
+        if (phase_timing) cudaEventRecord(pe[1], st);
+        // the queues are complete.  The Straus kernel goes first so that its CTAs are placed first; the
+        // (slow, rare) exact lanes follow on the side stream in single-warp CTAs that fit next to it.  All
+        // three kernels write disjoint ok[] lanes.
         CU(ctx, cudaEventRecord(ws->ev_fork, st));
-        CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
-        bjjk::verify_exact(ctx->sms * 4, ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, msg + o, ok + off, q, ctx->comb);
-        ctx->launches++;
-        CU(ctx, cudaGetLastError());
-        CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
         bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, s + o, 1, 0, ax + o, ay + o, hm, ok + off, ws->table, ctx->comb);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
+        CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+        bjjk::verify_exact(ctx->sms * 8, ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr, ctx->comb);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
+        if (phase_timing) cudaEventRecord(pe[2], st);
         CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
+        if (phase_timing) {
+            cudaEventRecord(pe[3], st);
+            cudaEventSynchronize(pe[3]);
+            float t_hash, t_ec, t_join;
+            cudaEventElapsedTime(&t_hash, pe[0], pe[1]);
+            cudaEventElapsedTime(&t_ec, pe[1], pe[2]);
+            cudaEventElapsedTime(&t_join, pe[2], pe[3]);
+            fprintf(stderr, "[bjj phase] lanes=%zu grid_h=%d grid_e=%d hash=%.3f ms ec(+overlapped exact)=%.3f ms join=%.3f ms\n", m, grid_h,
+                    grid_e, t_hash, t_ec, t_join);
+            for (int e = 0; e < 4; e++) cudaEventDestroy(pe[e]);
+        }
     }
     return BJJ_OK;
 }
@@ -495,7 +519,7 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
                               dax, day, status + off);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, ctx->flags_dev);
+        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, q, ctx->flags_dev);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         bjjk::verify_ec(grid_e, st, m, dx, dy, sig64 + 2 * o, 2, 1, dax, day, hm, ok + off, ws->table, ctx->comb);

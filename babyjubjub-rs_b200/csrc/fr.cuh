@@ -372,32 +372,33 @@ BJJ_HD void macn(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3
 #endif
 }
 
-// Montgomery reduction of a 512-bit value T (16 limbs, T < 2Q * 2^256):  r = T / 2^256 mod Q, r < 2Q.
-// The m_i * Q products go into two fresh accumulators (even / odd limbs of Q, so every chain is
-// carry-clean and every chain top lands in an empty column); T itself is only read.
+// Montgomery reduction of a 512-bit value T (16 limbs, T < 2^256 * 1.2 Q):  r = T / 2^256 mod Q, r < 2Q.
+// redc(T) = mont_mul(T_lo, 1) + T_hi: the accumulators start as (X, Y) = (T_lo, 0) and run the eight
+// reduction-only steps of fr_mul (same column bounds: every chain top lands in an empty column); the
+// upper half of T is added once at the end.
 BJJ_HD void fr_redc16(Fr& r, const uint32_t* T) {
     uint32_t X[18], Y[18];
 #pragma unroll
-    for (int i = 0; i < 18; i++) X[i] = Y[i] = 0;
-    uint32_t c = 0;                                    // carry of the previous column (0..3)
+    for (int i = 0; i < 18; i++) {
+        X[i] = i < 8 ? T[i] : 0;
+        Y[i] = 0;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         uint32_t* S = (i & 1) ? Y : X;                 // chain that starts at column i
         uint32_t* N = (i & 1) ? X : Y;
-        const uint32_t m = (T[i] + S[i] + N[i] + c) * BJJ_NINV32;
-        mac4<false, 1>(&S[i], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);
+        // carry of column i-1: X[i-1] + Y[i-1] is 0 or 2^32
+        const uint32_t c = i ? (((X[i ? i - 1 : 0] | Y[i ? i - 1 : 0]) != 0) ? 1u : 0u) : 0u;
+        const uint32_t m = (S[i] + N[i] + c) * BJJ_NINV32;
+        if (i == 0)
+            mac4<false, 1>(&S[i], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);
+        else
+            mac4<true, 1>(&S[i], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m, X[i ? i - 1 : 0], Y[i ? i - 1 : 0]);
         mac4<false, 0>(&N[i + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);
-        const uint64_t col = (uint64_t)T[i] + S[i] + N[i] + c;     // == 0 mod 2^32
-        c = (uint32_t)(col >> 32);
     }
-    // r = T[8..15] + X[8..15] + Y[8..15] + c
-    uint32_t u[8], cc[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) cc[i] = 0;
-    cc[0] = c;
-    add256(u, X + 8, Y + 8);
-    add256(u, u, T + 8);
-    add256(r.v, u, cc);
+    Fr u;
+    fr_merge_xy(u, X, Y);
+    add256(r.v, u.v, T + 8);
 }
 
 BJJ_HD void fr_sqr_dedicated(Fr& r, const Fr& a) {
@@ -462,7 +463,7 @@ BJJ_HD void fr_sqr_dedicated(Fr& r, const Fr& a) {
 
 // Measured on B200 (profiles/r1_imad_bench.jsonl): the dedicated squaring saves 28 of 128 IMAD.WIDE but
 // ptxas spends the difference on carry-flag traffic (P2R / IMAD.X / IMAD.MOV on the same fma pipe), so
-// it is not faster than fr_mul(a, a): 63.7 vs 68.3 G/s.  Kept selectable for the next tuning round.
+// it is not faster than fr_mul(a, a): v2 (single-chain redc) reaches 70-75 vs 68.3 G/s in isolation but costs registers: in k_verify_hash / k_verify_ec it was a net loss (13.1 vs 13.9 M verifies/s).  Kept selectable.
 #ifndef BJJ_DEDICATED_SQR
 #define BJJ_DEDICATED_SQR 0
 #endif

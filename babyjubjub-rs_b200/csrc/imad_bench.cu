@@ -14,6 +14,7 @@
 
 #include "fr.cuh"
 #include "fr29_proto.cuh"
+#include "fr52_proto.cuh"
 
 using namespace bjj;
 
@@ -117,6 +118,31 @@ __global__ void k_fr29(uint32_t* out, int iters, uint32_t seed) {
     if (s == 0x1234567) out[0] = s;
 }
 
+template <int ILP>
+__global__ void k_fr52(uint32_t* out, int iters, uint32_t seed) {
+    bjj52::Fr52 x[ILP], y[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            x[k].v[i] = (double)(((uint64_t)(seed + threadIdx.x * 977 + i * 131 + k) * 0x9E3779B97F4A7C15ull) >> 12);
+            y[k].v[i] = (double)(((uint64_t)(seed * 5 + blockIdx.x * 31 + i * 17 + k) * 0xC2B2AE3D27D4EB4Full) >> 12);
+        }
+        x[k].v[4] = (double)((uint64_t)x[k].v[4] >> 8);
+        y[k].v[4] = (double)((uint64_t)y[k].v[4] >> 8);
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) bjj52::mul(x[k], x[k], y[k]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int i = 0; i < 5; i++) s += x[k].v[i];
+    if (s == 1234567.0) out[0] = 1;
+}
+
 template <class K>
 static float time_kernel(K launch, int reps) {
     cudaEvent_t e0, e1;
@@ -190,6 +216,66 @@ int main(int argc, char** argv) {
             printf("{\"bench\": \"%s\", \"ilp\": %d, \"threads\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"gfmul_s\": %.2f}\n", \
                    NAME, ILP, threads, per_sm, ms, fm / ms / 1e6);                                                     \
         }                                                                                                              \
+    }
+    // sustained vs burst: the same fr_mul kernel for ~5 ms and for ~0.5 s (do clocks / power limit the long run?)
+    for (int mult : {1, 8, 64, 128}) {
+        const int threads = 256, grid = sms * 4, iters = 2048 * mult;
+        float ms = time_kernel([&]() { k_fr_mul<1, false><<<grid, threads>>>(out, iters, 777u); }, 2);
+        double fm = (double)grid * threads * iters;
+        printf("{\"bench\": \"fr_mul_sustained\", \"ms\": %.2f, \"gfmul_s\": %.2f}\n", ms, fm / ms / 1e6);
+    }
+    // FP64-pipe multiplier alone, and CONCURRENTLY with the IMAD multiplier (two streams): do the pipes overlap?
+    for (int threads : {128, 256}) {
+        for (int per_sm : {2, 4, 8}) {
+            if (threads * per_sm > 2048) continue;
+            const int grid = sms * per_sm;
+            const int iters = 2048;
+            float ms = time_kernel([&]() { k_fr52<1><<<grid, threads>>>(out, iters, 777u); }, 3);
+            double fm = (double)grid * threads * iters;
+            printf("{\"bench\": \"fr52_dfma_mul\", \"ilp\": 1, \"threads\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"gfmul_s\": %.2f}\n",
+                   threads, per_sm, ms, fm / ms / 1e6);
+            ms = time_kernel([&]() { k_fr52<2><<<grid, threads>>>(out, iters, 777u); }, 3);
+            printf("{\"bench\": \"fr52_dfma_mul\", \"ilp\": 2, \"threads\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"gfmul_s\": %.2f}\n",
+                   threads, per_sm, ms, 2 * fm / ms / 1e6);
+        }
+    }
+    {
+        cudaStream_t s1, s2;
+        CK(cudaStreamCreate(&s1));
+        CK(cudaStreamCreate(&s2));
+        uint32_t* out2;
+        CK(cudaMalloc(&out2, 64));
+        const int threads = 256, iters = 4096;
+        for (int per_sm : {1, 2, 3}) {
+            const int grid = sms * per_sm;
+            float t_imad = time_kernel([&]() { k_fr_mul<1, false><<<grid, threads, 0, s1>>>(out, iters, 777u); }, 3);
+            float t_dfma = time_kernel([&]() { k_fr52<1><<<grid, threads, 0, s2>>>(out2, iters, 777u); }, 3);
+            // both at once: events on the legacy stream bracket both streams via device sync
+            float best = 1e30f;
+            for (int rep = 0; rep < 3; rep++) {
+                CK(cudaDeviceSynchronize());
+                cudaEvent_t e0, e1;
+                CK(cudaEventCreate(&e0));
+                CK(cudaEventCreate(&e1));
+                CK(cudaEventRecord(e0, s1));
+                CK(cudaStreamWaitEvent(s2, e0, 0));
+                k_fr_mul<1, false><<<grid, threads, 0, s1>>>(out, iters, 777u);
+                k_fr52<1><<<grid, threads, 0, s2>>>(out2, iters, 777u);
+                cudaEvent_t j;
+                CK(cudaEventCreate(&j));
+                CK(cudaEventRecord(j, s2));
+                CK(cudaStreamWaitEvent(s1, j, 0));
+                CK(cudaEventRecord(e1, s1));
+                CK(cudaEventSynchronize(e1));
+                float ms;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (ms < best) best = ms;
+            }
+            double fm = (double)grid * threads * iters;
+            printf("{\"bench\": \"dual_pipe\", \"ctas_per_sm_each\": %d, \"ms_imad_alone\": %.3f, \"ms_dfma_alone\": %.3f, \"ms_both\": %.3f, "
+                   "\"gfmul_s_imad_alone\": %.2f, \"gfmul_s_dfma_alone\": %.2f, \"gfmul_s_both\": %.2f}\n",
+                   per_sm, t_imad, t_dfma, best, fm / t_imad / 1e6, fm / t_dfma / 1e6, 2 * fm / best / 1e6);
+        }
     }
     FRB29(1, false, "fr29_mul")
     FRB29(2, false, "fr29_mul")

@@ -11,11 +11,9 @@ using namespace bjj;
 // resident CTAs per SM the compiler must make room for (register cap = 65536 / (128 * MINB)); the carry
 // chains are dependent instruction streams, so the fma pipe needs >= 3-4 warps per SMSP to stay busy
 #ifndef BJJ_VERIFY_HASH_MINB
-#define BJJ_VERIFY_HASH_MINB 4
+#define BJJ_VERIFY_HASH_MINB 0
 #endif
-#ifndef BJJ_VERIFY_EC_MINB
-#define BJJ_VERIFY_EC_MINB 2
-#endif
+#define BJJ_VERIFY_EXACT_BLOCK 64
 
 __global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_pair(size_t n, const uint8_t* sig64, const uint8_t* pk32,
                                                                uint8_t* r8x, uint8_t* r8y, uint8_t* ax, uint8_t* ay,
@@ -23,16 +21,25 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_pair(size_t n, const u
     BJJ_LANE_LOOP(n) lane_decompress_pair(sig64, pk32, r8x, r8y, ax, ay, status, i);
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_HASH_MINB) k_verify_hash(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+#if BJJ_VERIFY_HASH_MINB > 0
+__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_HASH_MINB) k_verify_hash(
+#else
+__global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
+#endif
+    size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                            const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
                                                            const uint8_t* skip, uint8_t* hm, uint8_t* ok, int gate,
-                                                           ExactQueue q, uint32_t* gflags) {
+                                                           ExactQueue qa, ExactQueue qr, uint32_t* gflags) {
     BJJ_FLAGS_BEGIN
-    BJJ_LANE_LOOP(n) lane_verify_hash(r8x, r8y, ax, ay, msg, skip, hm, ok, i, gate != 0, q, flags);
+    BJJ_LANE_LOOP(n) lane_verify_hash(r8x, r8y, ax, ay, msg, skip, hm, ok, i, gate != 0, qa, qr, flags);
     BJJ_FLAGS_END(gflags)
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_EC_MINB) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+// Register budget left to the compiler (239 registers, 2 CTAs per SM): capping it at 168 for a third CTA
+// costs spills inside the Straus loop (measured 15.4 ms vs 11.7 ms per 2^18 lanes).  The register file is
+// partitioned per SMSP (16,384 registers each), so the exact-lane kernel cannot co-reside with this one
+// whatever the cap; it runs on a side stream and fills the tail instead.
+__global__ void __launch_bounds__(BJJ_BLOCK) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                          const uint8_t* s_base, size_t s_stride, size_t s_off,
                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                          uint8_t* ok, U128* table, const CombEntry* comb) {
@@ -40,11 +47,21 @@ __global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_EC_MINB) k_verify_ec(siz
     BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, i, tbl, comb);
 }
 
-// exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queue of k_verify_hash)
-__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
-                                                                  const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
-                                                                  uint8_t* ok, ExactQueue q, const CombEntry* comb) {
-    BJJ_QUEUE_LOOP(q) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, q.list[j], comb);
+// exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
+// One launch serves both queues: the first half of the grid takes the "A off the curve" queue, the second
+// half the "only R8 off the curve" queue, so no warp ever mixes the two ladders.
+__global__ void __launch_bounds__(BJJ_VERIFY_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
+                                                                         const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
+                                                                         uint8_t* ok, ExactQueue qa, ExactQueue qr,
+                                                                         const CombEntry* comb) {
+    const uint32_t half = gridDim.x / 2;
+    if (blockIdx.x < half) {
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *qa.count; j < cnt; j += half * blockDim.x)
+            lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb);
+    } else {
+        for (uint32_t j = (blockIdx.x - half) * blockDim.x + threadIdx.x, cnt = *qr.count; j < cnt; j += half * blockDim.x)
+            lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb);
+    }
 }
 
 namespace bjjk {
@@ -64,8 +81,8 @@ void decompress_pair(int grid, cudaStream_t st, size_t n, const uint8_t* sig64, 
 }
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
-                 ExactQueue q, uint32_t* gflags) {
-    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, skip, hm, ok, gate ? 1 : 0, q, gflags);
+                 ExactQueue qa, ExactQueue qr, uint32_t* gflags) {
+    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, skip, hm, ok, gate ? 1 : 0, qa, qr, gflags);
 }
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
                size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
@@ -73,8 +90,8 @@ void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const ui
     k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, table, comb);
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
-                  const uint8_t* ay, const uint8_t* msg, uint8_t* ok, ExactQueue q, const CombEntry* comb) {
-    k_verify_exact<<<grid, BJJ_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, msg, ok, q, comb);
+                  const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb) {
+    k_verify_exact<<<grid & ~1, BJJ_VERIFY_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, hm, ok, qa, qr, comb);
 }
 
 }  // namespace bjjk

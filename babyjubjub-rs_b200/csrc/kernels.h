@@ -47,12 +47,13 @@ void decompress_pair(int grid, cudaStream_t st, size_t n, const uint8_t* sig64, 
                      uint8_t* r8y, uint8_t* ax, uint8_t* ay, uint8_t* status);
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
-                 bjj::ExactQueue q, uint32_t* gflags);
+                 bjj::ExactQueue qa, bjj::ExactQueue qr, uint32_t* gflags);
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
                size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
                bjj::U128* table, const bjj::CombEntry* comb);
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
-                  const uint8_t* ay, const uint8_t* msg, uint8_t* ok, bjj::ExactQueue q, const bjj::CombEntry* comb);
+                  const uint8_t* ay, const uint8_t* hm, uint8_t* ok, bjj::ExactQueue qa, bjj::ExactQueue qr,
+                  const bjj::CombEntry* comb);
 void mul_scalar(int grid, cudaStream_t st, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
                 bjj::ProjScratch scr, bjj::U128* table, bjj::ExactQueue q, uint32_t* gflags);
 void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx,

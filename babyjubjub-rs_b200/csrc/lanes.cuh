@@ -753,26 +753,33 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAf
     return (fr_eq(lx, acc.X) && fr_eq(ly, acc.Y)) ? 1u : 0u;
 }
 
-// any A / R8 (also off the curve): src/lib.rs:395-412 operation for operation
-// Exact lane of verify: taken when R8 or A is not on the curve.  Every step whose inputs ARE curve
-// points still yields the group element the reference computes (complete addition law), so only the
-// off-curve parts replay the reference sequence:
+// Exact lanes of verify: taken when R8 or A is not on the curve (the hash kernel has already stored hm).
+// Every step whose inputs ARE curve points still yields the group element the reference computes
+// (complete addition law), so only the off-curve parts replay the reference sequence:
 //   l  = B8.mul_scalar(S)          B8 is on the curve            -> comb (same affine point)
-//   kA = A.mul_scalar(8*hm)        A on the curve  -> hm * (8A) by a table-free binary ladder
-//                                  A off the curve -> literal LSB-first double-and-add (src/lib.rs:149-164)
+//   kA = A.mul_scalar(8*hm)        A on the curve  (A_OFF = false) -> hm * (8A) by a table-free binary ladder
+//                                  A off the curve (A_OFF = true)  -> literal LSB-first double-and-add
+//                                                                      (src/lib.rs:149-164)
 //   r  = R8 + kA, affine           literal add-2008-bbjlp + affine (Z == 0 -> (0,0)), src/lib.rs:407-411
-BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& msg_m,
+// The two cases are queued separately so a warp never executes both ladders.
+template <bool A_OFF>
+BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& hm,
                              const CombEntry* comb) {
-    Fr hm;
-    verify_hm(hm, r8, a, msg_m);
     PointAff l, ka, ra;
-    PointExt acc;
-    PointProj pj;
-    fixed_base_comb(acc, comb, s);
-    ext_to_proj(pj, acc);
-    proj_affine(l, pj);
-    if (on_curve(a)) {
-        PointExt p8;
+    PointExt accl;
+    PointProj pl;
+    fixed_base_comb(accl, comb, s);
+    ext_to_proj(pl, accl);
+    if (A_OFF) {
+        proj_affine(l, pl);
+        uint32_t k9[9];
+        k9[0] = hm.v[0] << 3;
+#pragma unroll
+        for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
+        k9[8] = hm.v[7] >> 29;
+        mul_scalar_exact(ka, a, k9, 9);
+    } else {
+        PointExt p8, acc;
         ext_from_affine(p8, a);
         ext_dbl<false>(p8, p8);
         ext_dbl<false>(p8, p8);
@@ -785,45 +792,29 @@ BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointA
             ext_dbl<true>(acc, acc);
             if ((hm.v[i >> 5] >> (i & 31)) & 1) ext_add_niels<false>(acc, acc, n8);
         }
-        ext_to_proj(pj, acc);
-        proj_affine(ka, pj);
-    } else {
-        uint32_t k9[9];
-        k9[0] = hm.v[0] << 3;
-#pragma unroll
-        for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
-        k9[8] = hm.v[7] >> 29;
-        mul_scalar_exact(ka, a, k9, 9);
+        PointProj pk;
+        ext_to_proj(pk, acc);
+        // both Z are non-zero (complete formulas on curve points): one shared inversion
+        Fr t, ti, zl, zk;
+        fr_mul(t, pl.z, pk.z);
+        fr_inv(ti, t);
+        fr_mul(zl, ti, pk.z);
+        fr_mul(zk, ti, pl.z);
+        fr_mul(l.x, pl.x, zl);
+        fr_mul(l.y, pl.y, zl);
+        fr_mul(ka.x, pk.x, zk);
+        fr_mul(ka.y, pk.y, zk);
     }
-    PointProj pr, pk, sum;
+    PointProj pr, pk2, sum;
     pr.x = r8.x;
     pr.y = r8.y;
     pr.z = fr_const(BJJ_ONE_M);
-    pk.x = ka.x;
-    pk.y = ka.y;
-    pk.z = fr_const(BJJ_ONE_M);
-    proj_add_bbjlp(sum, pr, pk);
+    pk2.x = ka.x;
+    pk2.y = ka.y;
+    pk2.z = fr_const(BJJ_ONE_M);
+    proj_add_bbjlp(sum, pr, pk2);
     proj_affine(ra, sum);
     return (fr_eq(l.x, ra.x) && fr_eq(l.y, ra.y)) ? 1u : 0u;
-}
-
-// loads one verify lane; returns false when msg > Q (reference: `false` before anything else, src/lib.rs:396)
-BJJ_HD bool verify_load(PointAff& r8, uint32_t* s, PointAff& a, Fr& mm, const uint8_t* r8x, const uint8_t* r8y,
-                        const uint8_t* s32, const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, size_t i,
-                        uint32_t& flags) {
-    uint32_t msg[8];
-    load_u256(msg, msg32, i);
-    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
-    if (u256_lt(q, msg)) return false;     // msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
-    load_u256(s, s32, i);
-    load_fr(r8.x, r8x, i, flags);
-    load_fr(r8.y, r8y, i, flags);
-    load_fr(a.x, ax, i, flags);
-    load_fr(a.y, ay, i, flags);
-    Fr mraw;
-    fr_set(mraw, msg);
-    fr_to_mont(mm, mraw);
-    return true;
 }
 
 // verify runs as a short pipeline of kernels so that no kernel carries another phase's registers or code:
@@ -835,7 +826,7 @@ BJJ_HD bool verify_load(PointAff& r8, uint32_t* s, PointAff& a, Fr& mm, const ui
 #define BJJ_OK_PENDING 2
 BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
                              const uint8_t* msg32, const uint8_t* skip, uint8_t* hm_out, uint8_t* ok, size_t i,
-                             bool gate, const ExactQueue& q, uint32_t& flags) {
+                             bool gate, const ExactQueue& qa, const ExactQueue& qr, uint32_t& flags) {
     if (skip && skip[i]) {
         ok[i] = 0;
         return;
@@ -852,17 +843,23 @@ BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8
     load_fr(r8.y, r8y, i, flags);
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
-    if (gate && !(on_curve(a) && on_curve(r8))) {
-        ok[i] = 0;
-        exact_push(q, i);
-        return;
+    uint32_t state = BJJ_OK_PENDING;
+    if (gate) {
+        // off-curve lanes are queued for the exact kernels (by case, so their warps do not diverge)
+        if (!on_curve(a)) {
+            exact_push(qa, i);
+            state = 0;
+        } else if (!on_curve(r8)) {
+            exact_push(qr, i);
+            state = 0;
+        }
     }
     Fr mraw, mm, hm;
     fr_set(mraw, msg);
     fr_to_mont(mm, mraw);
     verify_hm(hm, r8, a, mm);
     store_u256(hm_out, i, hm.v);
-    ok[i] = BJJ_OK_PENDING;
+    ok[i] = (uint8_t)state;
 }
 
 // S of lane i sits at 32-byte element index i * s_stride + s_off (1, 0 for a plain S array; 2, 1 inside sig64)
@@ -882,16 +879,19 @@ BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t
     ok[i] = (uint8_t)verify_fast(r8, s, a, hm, tbl, comb);
 }
 
+template <bool A_OFF>
 BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
-                              const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, size_t i, const CombEntry* comb) {
+                              const uint8_t* ay, const uint8_t* hm_in, uint8_t* ok, size_t i, const CombEntry* comb) {
     uint32_t s[8], flags = 0;
     PointAff r8, a;
-    Fr mm;
-    if (!verify_load(r8, s, a, mm, r8x, r8y, s32, ax, ay, msg32, i, flags)) {
-        ok[i] = 0;
-        return;
-    }
-    ok[i] = (uint8_t)verify_exact(r8, s, a, mm, comb);
+    Fr hm;
+    load_u256(s, s32, i);
+    load_u256(hm.v, hm_in, i);
+    load_fr(r8.x, r8x, i, flags);
+    load_fr(r8.y, r8y, i, flags);
+    load_fr(a.x, ax, i, flags);
+    load_fr(a.y, ay, i, flags);
+    ok[i] = (uint8_t)verify_exact<A_OFF>(r8, s, a, hm, comb);
 }
 
 // decompress_signature + decompress(pk) (src/lib.rs:260-268, 192-224): phase 0 of verify_compressed.

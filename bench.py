@@ -132,13 +132,13 @@ def _from_int(v):
     return np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint8)
 
 
-def corrupt(cols, seed):
+def corrupt(cols, seed, denom=10):
     """cols = [r8x, r8y, s, ax, ay, msg] numpy (n,32) arrays, modified in place.  Returns (expected_ok, class_id)
     where class_id = -1 for untouched lanes."""
     n = len(cols[0])
     rng = np.random.default_rng(seed)
-    h = rng.integers(0, 10, size=n)
-    cls = np.where(h == 0, rng.integers(0, len(CORRUPTIONS), size=n), -1)
+    h = rng.integers(0, max(denom, 1), size=n)
+    cls = np.where((h == 0) & (denom > 0), rng.integers(0, len(CORRUPTIONS), size=n), -1)
     expected = np.ones(n, dtype=np.uint8)
     r8x, r8y, s, ax, ay, msg = cols
     orig = [c.copy() for c in (r8x, r8y, ax, ay)]
@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-lanes", type=int, default=21, help="signatures per GPU (2^21 x 8 GPUs = config 4's 2^24)")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--corrupt-denominator", type=int, default=10,
+                    help="1 lane in this many is corrupted (default 10 = the 10 %% of config 4; 0 = none, for diagnosis)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -288,7 +290,7 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     assert int(st.max().item()) == 0
     cols_h = [t.cpu().numpy() for t in (r8x, r8y, s, ax, ay, msgs)]
-    expected, cls = corrupt(cols_h, 0xC0DE + rank)
+    expected, cls = corrupt(cols_h, 0xC0DE + rank, args.corrupt_denominator)
     pinned = [torch.from_numpy(c).pin_memory() for c in cols_h]
     cols_d = [p.to(dev, non_blocking=True) for p in pinned]
     ok_d = torch.zeros(n, dtype=torch.uint8, device=dev)

@@ -15,8 +15,16 @@ using namespace bjj;
 static CombEntry* g_comb = nullptr;
 static std::vector<U128> g_table(BJJ_TABLE_U128_PER_LANE);
 
-static std::vector<uint32_t> g_list;
-static uint32_t g_count;
+static std::vector<uint32_t> g_list, g_list2;
+static uint32_t g_count, g_count2;
+static ExactQueue exact_queue2(size_t n) {
+    g_list2.assign(n + 1, 0);
+    g_count2 = 0;
+    ExactQueue q;
+    q.count = &g_count2;
+    q.list = g_list2.data();
+    return q;
+}
 static ExactQueue exact_queue(size_t n) {
     g_list.assign(n + 1, 0);
     g_count = 0;
@@ -162,11 +170,12 @@ uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint
                     const uint8_t* ay, const uint8_t* msg, uint8_t* ok) {
     emu_init();
     uint32_t flags = 0;
-    ExactQueue q = exact_queue(n);
+    ExactQueue qa = exact_queue(n), qr = exact_queue2(n);
     std::vector<uint8_t> hm(32 * (n + 1));
-    for (size_t i = 0; i < n; i++) lane_verify_hash(r8x, r8y, ax, ay, msg, nullptr, hm.data(), ok, i, true, q, flags);
+    for (size_t i = 0; i < n; i++) lane_verify_hash(r8x, r8y, ax, ay, msg, nullptr, hm.data(), ok, i, true, qa, qr, flags);
     for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, s, 1, 0, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
-    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact(r8x, r8y, s, ax, ay, msg, ok, g_list[j], g_comb);
+    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list[j], g_comb);
+    for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list2[j], g_comb);
     return flags;
 }
 
@@ -178,7 +187,7 @@ void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, 
     uint32_t flags = 0;
     ExactQueue q = exact_queue(n);
     for (size_t i = 0; i < n; i++) lane_decompress_pair(sig64, pk32, dx, dy, ax, ay, status, i);
-    for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, flags);
+    for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, q, flags);
     for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, sig64, 2, 1, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
 }
 
