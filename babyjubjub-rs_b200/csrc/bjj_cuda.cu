@@ -76,9 +76,20 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_compress(size_t n, const uint8_t*
     BJJ_FLAGS_END(gflags)
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress(size_t n, const uint8_t* in, uint8_t* rx, uint8_t* ry,
-                                                          uint8_t* status) {
-    BJJ_LANE_LOOP(n) lane_decompress(in, rx, ry, status, i);
+// decompress_point in three phases around ONE shared inversion per thread (lanes.cuh): prepare (u, v) ->
+// batched inverse of v -> square root + sign rule.  `slot0` offsets the scratch slots so that the R8 and A
+// points of verify_compressed share one inversion pass.
+__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_prepare(size_t n, const uint8_t* in, size_t stride, size_t off,
+                                                                  ProjScratch scr, size_t slot0) {
+    BJJ_LANE_LOOP(n) lane_decompress_prepare(in, stride, off, scr, slot0 + i, i);
+}
+__global__ void __launch_bounds__(BJJ_BLOCK) k_batch_inverse(size_t n, ProjScratch scr) {
+    batch_inverse_strided(scr, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_finish(size_t n, const uint8_t* in, size_t stride, size_t off,
+                                                                 ProjScratch scr, size_t slot0, uint8_t* rx, uint8_t* ry,
+                                                                 uint8_t* status, int merge) {
+    BJJ_LANE_LOOP(n) lane_decompress_finish(in, stride, off, scr, slot0 + i, rx, ry, status, i, merge != 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -427,6 +438,28 @@ static int launch_fixed_base(bjj_ctx* ctx, size_t n, const uint8_t* in, uint8_t*
     }
     return BJJ_OK;
 }
+static int launch_decompress(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* rx, uint8_t* ry, uint8_t* status,
+                             cudaStream_t st, Workspace* ws) {
+    for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
+        const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
+        const size_t o = 32 * off;
+        ProjScratch scr;
+        int rc = ensure_proj(ctx, ws, n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &scr);
+        if (rc) return rc;
+        k_decompress_prepare<<<grid_for(ctx, (const void*)k_decompress_prepare, m), BJJ_BLOCK, 0, st>>>(m, in32 + o, 1, 0, scr, 0);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        k_batch_inverse<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        k_decompress_finish<<<grid_for(ctx, (const void*)k_decompress_finish, m), BJJ_BLOCK, 0, st>>>(m, in32 + o, 1, 0, scr, 0, rx + o,
+                                                                                                     ry + o, status + off, 0);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return BJJ_OK;
+}
+
 // verify scratch: hm (32 B / lane) and, for the compressed pipeline, the four decompressed coordinates
 static int ensure_vscratch(bjj_ctx* ctx, Workspace* ws, size_t lanes, uint8_t** hm, uint8_t** pts) {
     if (ws->vs_lanes < lanes) {
@@ -515,9 +548,18 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         if (rc) return rc;
         const size_t L = 32 * ws->vs_lanes;
         uint8_t *dx = pts, *dy = pts + L, *dax = pts + 2 * L, *day = pts + 3 * L;
-        bjjk::decompress_pair(grid_cap(ctx, bjjk::decompress_pair_blocks_per_sm(), m), st, m, sig64 + 2 * o, pk32 + o, dx, dy,
-                              dax, day, status + off);
-        ctx->launches++;
+        // phase 0: decompress R8 (first half of each 64-byte signature) and A with one shared inversion pass
+        ProjScratch scr;
+        rc = ensure_proj(ctx, ws, 2 * (n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m), &scr);
+        if (rc) return rc;
+        const int grid_p = grid_for(ctx, (const void*)k_decompress_prepare, m);
+        const int grid_f = grid_for(ctx, (const void*)k_decompress_finish, m);
+        k_decompress_prepare<<<grid_p, BJJ_BLOCK, 0, st>>>(m, sig64 + 2 * o, 2, 0, scr, 0);
+        k_decompress_prepare<<<grid_p, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m);
+        k_batch_inverse<<<affine_grid(ctx, 2 * m), BJJ_BLOCK, 0, st>>>(2 * m, scr);
+        k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, sig64 + 2 * o, 2, 0, scr, 0, dx, dy, status + off, 0);
+        k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m, dax, day, status + off, 1);
+        ctx->launches += 5;
         CU(ctx, cudaGetLastError());
         bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, q, ctx->flags_dev);
         ctx->launches++;
@@ -609,8 +651,7 @@ int bjj_decompress_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_
                              void* stream) {
     DEV_PROLOGUE
     if (!in32 || !rx || !ry || !status) return BJJ_ERR_ARG;
-    k_decompress<<<grid_for(ctx, (const void*)k_decompress, n), BJJ_BLOCK, 0, st>>>(n, in32, rx, ry, status);
-    DEV_EPILOGUE
+    return launch_decompress(ctx, n, in32, rx, ry, status, st, &ctx->ws);
 }
 
 int bjj_poseidon_batch_dev(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out, void* stream) {
@@ -792,8 +833,7 @@ int bjj_decompress_batch(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* r
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(in32, 32), H_OUT(rx, 32), H_OUT(ry, 32), H_OUT(status, 1)};
     return run_host(ctx, n, args, 4, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        k_decompress<<<grid_for(ctx, (const void*)k_decompress, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3]);
-        CHECK_LAUNCH(ctx)
+        return launch_decompress(ctx, m, d[0], d[1], d[2], d[3], sl.stream, &sl.ws);
     });
 }
 

@@ -3,7 +3,8 @@
 //
 // One verification is a short pipeline of kernels, so that no kernel carries another phase's registers
 // or instruction footprint:
-//   k_decompress_pair (compressed input only) -> k_verify_hash -> k_verify_ec -> k_verify_exact
+//   (bjj_cuda.cu: k_decompress_prepare / k_batch_inverse / k_decompress_finish for compressed input) ->
+//   k_verify_hash -> k_verify_ec || k_verify_exact
 #include "kernels.h"
 
 using namespace bjj;
@@ -14,12 +15,6 @@ using namespace bjj;
 #define BJJ_VERIFY_HASH_MINB 0
 #endif
 #define BJJ_VERIFY_EXACT_BLOCK 64
-
-__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_pair(size_t n, const uint8_t* sig64, const uint8_t* pk32,
-                                                               uint8_t* r8x, uint8_t* r8y, uint8_t* ax, uint8_t* ay,
-                                                               uint8_t* status) {
-    BJJ_LANE_LOOP(n) lane_decompress_pair(sig64, pk32, r8x, r8y, ax, ay, status, i);
-}
 
 #if BJJ_VERIFY_HASH_MINB > 0
 __global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_HASH_MINB) k_verify_hash(
@@ -73,12 +68,7 @@ static int occ(const void* k, int block) {
 }
 int verify_hash_blocks_per_sm() { return occ((const void*)k_verify_hash, BJJ_BLOCK); }
 int verify_ec_blocks_per_sm() { return occ((const void*)k_verify_ec, BJJ_BLOCK); }
-int decompress_pair_blocks_per_sm() { return occ((const void*)k_decompress_pair, BJJ_BLOCK); }
 
-void decompress_pair(int grid, cudaStream_t st, size_t n, const uint8_t* sig64, const uint8_t* pk32, uint8_t* r8x,
-                     uint8_t* r8y, uint8_t* ax, uint8_t* ay, uint8_t* status) {
-    k_decompress_pair<<<grid, BJJ_BLOCK, 0, st>>>(n, sig64, pk32, r8x, r8y, ax, ay, status);
-}
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
                  ExactQueue qa, ExactQueue qr, uint32_t* gflags) {

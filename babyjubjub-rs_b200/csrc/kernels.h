@@ -38,13 +38,10 @@ namespace bjjk {
 // resident CTAs per SM of the kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor), >= 1
 int verify_hash_blocks_per_sm();
 int verify_ec_blocks_per_sm();
-int decompress_pair_blocks_per_sm();
 int mul_scalar_blocks_per_sm();
 int sign_blocks_per_sm();
 int poseidon_blocks_per_sm(int t);
 
-void decompress_pair(int grid, cudaStream_t st, size_t n, const uint8_t* sig64, const uint8_t* pk32, uint8_t* r8x,
-                     uint8_t* r8y, uint8_t* ax, uint8_t* ay, uint8_t* status);
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
                  bjj::ExactQueue qa, bjj::ExactQueue qr, uint32_t* gflags);

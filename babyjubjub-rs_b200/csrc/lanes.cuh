@@ -491,11 +491,14 @@ BJJ_HD uint32_t ph_lookup(const Fr& t) {
 // the order-2^28 subgroup; its discrete log k is found 7 bits at a time (Pohlig-Hellman with table
 // look-ups) and x = x0 * g^(-k/2).  The returned x does not depend on which root a sqrt algorithm finds
 // (src/lib.rs:217-220 fixes the sign), so the result is bit-identical.
-BJJ_HD uint32_t decompress_core(Fr& xm, Fr& ym, const uint32_t* bytes) {
+// The decompression is split around the one modular inverse so that a batch can share it
+// (Montgomery's trick, lanes.cuh::batch_inverse_strided):
+//   decompress_prepare: range check, u = 1 - y^2, v = a - d y^2           -> status, y, u, v
+//   decompress_finish : x^2 = u / v, fixed-schedule square root, sign rule -> status, x
+BJJ_HD uint32_t decompress_prepare(Fr& ym, Fr& u, Fr& v, const uint32_t* bytes) {
     uint32_t yw[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) yw[i] = bytes[i];
-    const bool sign = (yw[7] >> 31) != 0;
     yw[7] &= 0x7FFFFFFFu;
     const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
     if (!u256_lt(yw, q)) return BJJ_ST_Y_RANGE;
@@ -503,14 +506,18 @@ BJJ_HD uint32_t decompress_core(Fr& xm, Fr& ym, const uint32_t* bytes) {
     fr_set(yraw, yw);
     fr_to_mont(ym, yraw);
     const Fr one = fr_const(BJJ_ONE_M), cA = fr_const(BJJ_A_M), cD = fr_const(BJJ_D_M);
-    Fr y2, u, v, vi, a;
+    Fr y2;
     fr_sqr(y2, ym);
     fr_sub(u, one, y2);
     fr_mul(v, cD, y2);
     fr_sub(v, cA, v);
     if (fr_is_zero(v)) return BJJ_ST_NO_INV;
-    fr_inv(vi, v);
-    fr_mul(a, u, vi);
+    return BJJ_ST_OK;
+}
+
+BJJ_HD uint32_t decompress_finish(Fr& xm, bool sign, const Fr& u, const Fr& vinv) {
+    Fr a;
+    fr_mul(a, u, vinv);
     if (fr_is_zero(a)) return BJJ_ST_NOT_SQUARE;     // modsqrt rejects a == 0 (src/utils.rs:118)
     Fr w, x0, b, t;
     fr_pow(w, a, BJJ_EXP_TM1H, BJJ_EXP_TM1H_BITS);
@@ -539,6 +546,93 @@ BJJ_HD uint32_t decompress_core(Fr& xm, Fr& ym, const uint32_t* bytes) {
     if (big != sign) fr_neg(x0, x0);
     xm = x0;
     return BJJ_ST_OK;
+}
+
+// single-lane composition (exact lanes, tests): one Fermat inverse
+BJJ_HD uint32_t decompress_core(Fr& xm, Fr& ym, const uint32_t* bytes) {
+    Fr u, v, vi;
+    uint32_t st = decompress_prepare(ym, u, v, bytes);
+    if (st != BJJ_ST_OK) return st;
+    fr_inv(vi, v);
+    return decompress_finish(xm, (bytes[7] >> 31) != 0, u, vi);
+}
+
+// Batched form.  Compressed point of lane i = 32-byte element i * stride + off of `in` (1, 0 for a plain
+// array; 2, 0 for the R8 half of sig64).  Phase 1 parks u, v (v = 0 for rejected lanes) and the early
+// status (one byte per slot in the scratch's y area) in scratch.
+BJJ_HD void lane_decompress_prepare(const uint8_t* in, size_t stride, size_t off, const ProjScratch& scr, size_t slot,
+                                    size_t i) {
+    uint32_t b[8];
+    load_u256(b, in, i * stride + off);
+    Fr y, u, v;
+    fr_zero(u);
+    fr_zero(v);
+    uint32_t st = decompress_prepare(y, u, v, b);
+    if (st != BJJ_ST_OK) fr_zero(v);
+    store_u256(scr.x, slot, u.v);
+    store_u256(scr.z, slot, v.v);
+    scr.y[slot] = (uint8_t)st;
+}
+
+// in-place inversion of scr.z[t], scr.z[t+T], ... (zeros stay zero); one Fermat inversion per thread
+BJJ_HD void batch_inverse_strided(const ProjScratch& s, size_t n, size_t t, size_t T) {
+    if (t >= n) return;
+    const Fr one = fr_const(BJJ_ONE_M);
+    Fr acc = one, z;
+    size_t last = t;
+#pragma unroll 1
+    for (size_t i = t; i < n; i += T) {
+        load_u256(z.v, s.z, i);
+        if (!fr_is_zero(z)) fr_mul(acc, acc, z);
+        store_u256(s.p, i, acc.v);
+        last = i;
+    }
+    Fr inv;
+    fr_inv(inv, acc);
+#pragma unroll 1
+    for (size_t i = last;; i -= T) {
+        Fr prev = one, zi;
+        if (i >= t + T) load_u256(prev.v, s.p, i - T);
+        load_u256(z.v, s.z, i);
+        if (!fr_is_zero(z)) {
+            fr_mul(zi, inv, prev);
+            fr_mul(inv, inv, z);
+            store_u256(s.z, i, zi.v);
+        }
+        if (i < t + T) break;
+    }
+}
+
+// Phase 3: x from (u, 1/v).  `merge` (second point of verify_compressed): an earlier error of the same
+// lane (R8 is decoded first) wins, as in decompress_signature followed by decompress_point.
+BJJ_HD void lane_decompress_finish(const uint8_t* in, size_t stride, size_t off, const ProjScratch& scr, size_t slot,
+                                   uint8_t* rx, uint8_t* ry, uint8_t* status, size_t i, bool merge) {
+    uint32_t own = scr.y[slot];
+    Fr x, y;
+    fr_zero(x);
+    fr_zero(y);
+    if (own == BJJ_ST_OK) {
+        uint32_t b[8];
+        load_u256(b, in, i * stride + off);
+        const bool sign = (b[7] >> 31) != 0;
+        b[7] &= 0x7FFFFFFFu;
+        Fr yraw, u, vi;
+        fr_set(yraw, b);
+        fr_to_mont(y, yraw);
+        load_u256(u.v, scr.x, slot);
+        load_u256(vi.v, scr.z, slot);
+        own = decompress_finish(x, sign, u, vi);
+        if (own != BJJ_ST_OK) {
+            fr_zero(x);
+            fr_zero(y);
+        }
+    }
+    store_fr(rx, i, x);
+    store_fr(ry, i, y);
+    if (!merge)
+        status[i] = (uint8_t)own;
+    else if (status[i] == BJJ_ST_OK)
+        status[i] = (uint8_t)own;
 }
 
 BJJ_HD void lane_decompress(const uint8_t* in, uint8_t* rx, uint8_t* ry, uint8_t* status, size_t i) {
@@ -892,29 +986,6 @@ BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
     ok[i] = (uint8_t)verify_exact<A_OFF>(r8, s, a, hm, comb);
-}
-
-// decompress_signature + decompress(pk) (src/lib.rs:260-268, 192-224): phase 0 of verify_compressed.
-// sig64 = compress(R8) || S_le32, pk32 = compress(A).  status = first decompression error (R8 first, then
-// A); the decompressed coordinates go to scratch as canonical bytes and the verify phases run on them
-// with the gate off (decompressed points are on the curve by construction).
-BJJ_HD void lane_decompress_pair(const uint8_t* sig64, const uint8_t* pk32, uint8_t* r8x, uint8_t* r8y, uint8_t* ax,
-                                 uint8_t* ay, uint8_t* status, size_t i) {
-    uint32_t rb[8], ab[8];
-    load_u256(rb, sig64, 2 * i);
-    load_u256(ab, pk32, i);
-    PointAff r8, a;
-    fr_zero(r8.x);
-    fr_zero(r8.y);
-    fr_zero(a.x);
-    fr_zero(a.y);
-    uint32_t st = decompress_core(r8.x, r8.y, rb);
-    if (st == BJJ_ST_OK) st = decompress_core(a.x, a.y, ab);
-    status[i] = (uint8_t)st;
-    store_fr(r8x, i, r8.x);
-    store_fr(r8y, i, r8.y);
-    store_fr(ax, i, a.x);
-    store_fr(ay, i, a.y);
 }
 
 }  // namespace bjj

@@ -144,8 +144,17 @@ uint32_t emu_compress(size_t n, const uint8_t* px, const uint8_t* py, uint8_t* o
     return flags;
 }
 
+// batched decompression exactly as the kernels sequence it: prepare -> batched inverse -> finish
+static void batch_inverse(const ProjScratch& s, size_t n) {
+    const size_t T = 3;
+    for (size_t t = 0; t < T; t++) batch_inverse_strided(s, n, t, T);
+}
+
 void emu_decompress(size_t n, const uint8_t* in, uint8_t* rx, uint8_t* ry, uint8_t* status) {
-    for (size_t i = 0; i < n; i++) lane_decompress(in, rx, ry, status, i);
+    ProjScratch scr = proj_scratch(n);
+    for (size_t i = 0; i < n; i++) lane_decompress_prepare(in, 1, 0, scr, i, i);
+    batch_inverse(scr, n);
+    for (size_t i = 0; i < n; i++) lane_decompress_finish(in, 1, 0, scr, i, rx, ry, status, i, false);
 }
 
 uint32_t emu_poseidon(int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out) {
@@ -186,7 +195,12 @@ void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, 
     uint8_t *dx = d.data(), *dy = dx + 32 * n, *ax = dy + 32 * n, *ay = ax + 32 * n;
     uint32_t flags = 0;
     ExactQueue q = exact_queue(n);
-    for (size_t i = 0; i < n; i++) lane_decompress_pair(sig64, pk32, dx, dy, ax, ay, status, i);
+    ProjScratch scr = proj_scratch(2 * n);
+    for (size_t i = 0; i < n; i++) lane_decompress_prepare(sig64, 2, 0, scr, i, i);
+    for (size_t i = 0; i < n; i++) lane_decompress_prepare(pk32, 1, 0, scr, n + i, i);
+    batch_inverse(scr, 2 * n);
+    for (size_t i = 0; i < n; i++) lane_decompress_finish(sig64, 2, 0, scr, i, dx, dy, status, i, false);
+    for (size_t i = 0; i < n; i++) lane_decompress_finish(pk32, 1, 0, scr, n + i, ax, ay, status, i, true);
     for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, q, flags);
     for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, sig64, 2, 1, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
 }

@@ -133,3 +133,46 @@ def test_multi_device_sharding(gpu, oracle_c):
     arrs = cases_to_arrays(signature_cases(random.Random(21), 5))
     ok = bjj.verify_batch_multi(mg, *arrs)
     assert np.array_equal(ok, oracle_c.verify(*arrs))
+
+
+def test_device_pointer_flavour_across_subbatches(gpu, oracle_c):
+    """the _dev entry points with more lanes than one internal sub-batch (2^21): sign -> public -> verify on
+    device-resident data, using only the library's own allocation / copy helpers (no torch)"""
+    import ctypes
+    eng = gpu.eng
+    lib, ctx = eng.lib, eng.ctx
+    n = (1 << 21) + 4321
+    rng = np.random.default_rng(7)
+    keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs[:, 31] &= 0x1F
+    msgs[5] = 0xFF                                  # msg > Q: sign status 4, verify false
+
+    def dev(nbytes):
+        p = lib.bjj_dev_alloc(ctx, nbytes)
+        assert p
+        return ctypes.c_void_p(p)
+    d = {k: dev(32 * n) for k in ("keys", "msgs", "r8x", "r8y", "s", "ax", "ay")}
+    d_st, d_ok = dev(n), dev(n)
+    try:
+        for name, arr in (("keys", keys), ("msgs", msgs)):
+            assert lib.bjj_memcpy_h2d(ctx, d[name], arr.ctypes.data_as(ctypes.c_void_p), 32 * n) == 0
+        assert lib.bjj_sign_batch_dev(ctx, n, d["keys"], d["msgs"], d["r8x"], d["r8y"], d["s"], d_st, None) == 0
+        assert lib.bjj_public_batch_dev(ctx, n, d["keys"], d["ax"], d["ay"], None) == 0
+        assert lib.bjj_verify_batch_dev(ctx, n, d["r8x"], d["r8y"], d["s"], d["ax"], d["ay"], d["msgs"], d_ok, None) == 0
+        ok = np.empty(n, dtype=np.uint8)
+        st = np.empty(n, dtype=np.uint8)
+        ax = np.empty((n, 32), dtype=np.uint8)
+        for dst, src, nb in ((ok, d_ok, n), (st, d_st, n), (ax, d["ax"], 32 * n)):
+            assert lib.bjj_memcpy_d2h(ctx, dst.ctypes.data_as(ctypes.c_void_p), src, nb) == 0
+        eng.sync()
+        assert st[5] == 4 and ok[5] == 0
+        mask = np.ones(n, dtype=bool)
+        mask[5] = False
+        assert st[mask].max() == 0 and ok[mask].all()          # every signature made on the device verifies
+        idx = np.concatenate([np.arange(8), np.arange((1 << 21) - 4, (1 << 21) + 4), np.arange(n - 8, n)])
+        ex, _ = oracle_c.public(keys[idx])
+        assert np.array_equal(ax[idx], ex)
+    finally:
+        for p in list(d.values()) + [d_st, d_ok]:
+            lib.bjj_dev_free(ctx, p)
