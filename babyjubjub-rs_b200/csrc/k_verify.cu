@@ -12,7 +12,7 @@ using namespace bjj;
 // resident CTAs per SM the compiler must make room for (register cap = 65536 / (128 * MINB)); the carry
 // chains are dependent instruction streams, so the fma pipe needs >= 3-4 warps per SMSP to stay busy
 #ifndef BJJ_VERIFY_HASH_MINB
-#define BJJ_VERIFY_HASH_MINB 0
+#define BJJ_VERIFY_HASH_MINB 2
 #endif
 #define BJJ_VERIFY_EXACT_BLOCK 64
 
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
 // costs spills inside the Straus loop (measured 15.4 ms vs 11.7 ms per 2^18 lanes).  The register file is
 // partitioned per SMSP (16,384 registers each), so the exact-lane kernel cannot co-reside with this one
 // whatever the cap; it runs on a side stream and fills the tail instead.
-__global__ void __launch_bounds__(BJJ_BLOCK) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                          const uint8_t* s_base, size_t s_stride, size_t s_off,
                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                          uint8_t* ok, U128* table, const CombEntry* comb) {
