@@ -55,12 +55,12 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_batch_affine(size_t n, ProjScratc
     batch_affine_strided(scr, rx, ry, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK) k_fixed_base(size_t n, const uint8_t* k, ProjScratch scr,
+__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_fixed_base(size_t n, const uint8_t* k, ProjScratch scr,
                                                           const CombEntry* comb) {
     BJJ_LANE_LOOP(n) lane_fixed_base(k, scr, i, comb);
 }
 
-__global__ void __launch_bounds__(BJJ_BLOCK) k_public(size_t n, const uint8_t* key, ProjScratch scr,
+__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_public(size_t n, const uint8_t* key, ProjScratch scr,
                                                       const CombEntry* comb) {
     BJJ_LANE_LOOP(n) lane_public(key, scr, i, comb);
 }
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_prepare(size_t n, cons
 __global__ void __launch_bounds__(BJJ_BLOCK) k_batch_inverse(size_t n, ProjScratch scr) {
     batch_inverse_strided(scr, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
-__global__ void __launch_bounds__(BJJ_BLOCK) k_decompress_finish(size_t n, const uint8_t* in, size_t stride, size_t off,
+__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_decompress_finish(size_t n, const uint8_t* in, size_t stride, size_t off,
                                                                  ProjScratch scr, size_t slot0, uint8_t* rx, uint8_t* ry,
                                                                  uint8_t* status, int merge) {
     BJJ_LANE_LOOP(n) lane_decompress_finish(in, stride, off, scr, slot0 + i, rx, ry, status, i, merge != 0);

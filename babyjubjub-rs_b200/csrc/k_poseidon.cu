@@ -4,7 +4,7 @@
 using namespace bjj;
 
 template <int T>
-__global__ void __launch_bounds__(BJJ_BLOCK) k_poseidon(size_t n, PoseidonIn in, uint8_t* out, uint32_t* gflags) {
+__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_poseidon(size_t n, PoseidonIn in, uint8_t* out, uint32_t* gflags) {
     BJJ_FLAGS_BEGIN
     BJJ_LANE_LOOP(n) lane_poseidon<T>(in.p, out, i, flags);
     BJJ_FLAGS_END(gflags)

@@ -3,7 +3,7 @@
 
 using namespace bjj;
 
-__global__ void __launch_bounds__(BJJ_BLOCK) k_sign(size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* r8x,
+__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_sign(size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* r8x,
                                                     uint8_t* r8y, uint8_t* s32, uint8_t* status, const CombEntry* comb) {
     BJJ_LANE_LOOP(n) lane_sign(key, msg, r8x, r8y, s32, status, i, comb);
 }
