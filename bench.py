@@ -377,10 +377,10 @@ def run_ours(args, rank, local_rank, world):
         "algorithmic_mac_per_verify": ALGO_MAC["verify"],
         "frac_at_observed_clock": (achieved / (sms * WIDE_MAC_LANES_PER_CLK_SM * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_verify_ec) per launch, from the
-        # ncu --set full capture at this workload size (profiles/r1_ncu_verify_final_summary.txt): 428.2 MB per
-        # 2^21 lanes = 204 B per lane, against 193 B per lane algorithmic (192 B in, 1 B out)
-        "traffic": int(n * 204.2),
-        "dominant_kernel": "k_verify_ec (Straus pass): 92.8 ms of a 139 ms step; fmaheavy pipe 85.9 % busy (ncu)",
+        # ncu --set full capture at this workload size (profiles/r1_ncu_verify_final_summary.txt): 431.2 MB per
+        # 2^21 lanes = 205.6 B per lane, against 193 B per lane algorithmic (192 B in, 1 B out)
+        "traffic": int(n * 205.6),
+        "dominant_kernel": "k_verify_ec (Straus pass): 92.9 ms of a 131 ms step; fmaheavy pipe 85.2 % busy (ncu)",
         "hbm": {"achieved_gbs": per_gpu * 193 / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind,
                 "note": "193 B per verify (6 x 32 B in, 1 B out); secondary counter, this path is not HBM-bound"},
     }
