@@ -176,3 +176,74 @@ def test_device_pointer_flavour_across_subbatches(gpu, oracle_c):
     finally:
         for p in list(d.values()) + [d_st, d_ok]:
             lib.bjj_dev_free(ctx, p)
+
+
+def test_config1_bench_workloads_1024(gpu, oracle_c):
+    """BASELINE config 1: the criterion workloads of benches/bench_babyjubjub.rs (add, mul_scalar_small,
+    mul_scalar, compress, decompress, sign, verify) on a 1,024-element synthetic batch, lane for lane
+    against the oracle.  Lane 0 carries the bench's own inputs (benches/bench_babyjubjub.rs:15-53)."""
+    import random
+    from common import P_KAT
+    n = 1024
+    rnd = random.Random(0xB200)
+    pts = [P_KAT] + [O.mul_scalar(O.B8, rnd.randrange(1 << 251)) for _ in range(63)]
+    pts = [pts[i % 64] for i in range(n)]
+    px, py = pack([p[0] for p in pts]), pack([p[1] for p in pts])
+    one = pack([1] * n)
+    # add (projective, bench: p + p)
+    qx, qy = np.roll(px, 1, axis=0), np.roll(py, 1, axis=0)
+    qx[0], qy[0] = px[0], py[0]
+    got, exp = gpu.add(px, py, one, qx, qy, one), oracle_c.add(px, py, one, qx, qy, one)
+    assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+    # mul_scalar_small (3) and mul_scalar (the bench's 251-bit scalar on lane 0, uniform 254-bit elsewhere)
+    k3 = pack([3] * n)
+    kb = pack([2626589144620713026669568689430873010625803728049924121243784502389097019475] +
+              [rnd.randrange(1 << 254) for _ in range(n - 1)])
+    for k in (k3, kb):
+        got, exp = gpu.mul_scalar(px, py, k), oracle_c.mul_scalar(px, py, k)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+    # compress / decompress
+    comp = gpu.compress(px, py)
+    assert np.array_equal(comp, oracle_c.compress(px, py))
+    dx, dy, st = gpu.decompress(comp)
+    assert not st.any() and np.array_equal(dx, px) and np.array_equal(dy, py)
+    # sign (msg = 5 on lane 0) and verify
+    keys = np.frombuffer(b"".join(rnd.randbytes(32) for _ in range(n)), dtype=np.uint8).reshape(n, 32)
+    msgs = pack([5] + [rnd.randrange(Q) for _ in range(n - 1)])
+    g = gpu.sign(keys, msgs)
+    e = oracle_c.sign(keys, msgs)
+    assert all(np.array_equal(a, b) for a, b in zip(g, e))
+    ax, ay = gpu.public(keys)
+    ok = gpu.verify(g[0], g[1], g[2], ax, ay, msgs)
+    assert ok.all() and np.array_equal(ok, oracle_c.verify(g[0], g[1], g[2], ax, ay, msgs))
+
+
+def test_verify_random_corruption_mix_vs_oracle(gpu, oracle_c):
+    """16,384 signatures with the benchmark's 10 % corruption mix (8 classes), every lane against the oracle"""
+    import importlib.util
+    import os
+    from common import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n = 1 << 14
+    rng = np.random.default_rng(99)
+    keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs[:, 31] &= 0x1F
+    rx, ry, s, st = gpu.sign(keys, msgs)
+    assert not st.any()
+    ax, ay = gpu.public(keys)
+    cols = [rx.copy(), ry.copy(), s.copy(), ax.copy(), ay.copy(), msgs.copy()]
+    expected, cls = bench.corrupt(cols, 1234, 4)          # 25 % corrupted: more lanes per class
+    assert all((cls == c).sum() > 100 for c in range(len(bench.CORRUPTIONS)))
+    ok = gpu.verify(*cols)
+    ref = oracle_c.verify(*cols)
+    assert np.array_equal(ok, ref)
+    assert np.array_equal(ok, expected)
+    # and the compressed pipeline on the same (decodable) signatures
+    sig64 = np.concatenate([gpu.compress(cols[0], cols[1]), cols[2]], axis=1)
+    pk32 = gpu.compress(cols[3], cols[4])
+    gok, gst = gpu.verify_compressed(sig64, pk32, cols[5])
+    eok, est = oracle_c.verify_compressed(sig64, pk32, cols[5])
+    assert np.array_equal(gst, est) and np.array_equal(gok, eok)
