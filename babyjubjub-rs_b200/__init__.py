@@ -195,6 +195,14 @@ class Engine:
         self._check(self.lib.bjj_verify_batch(self.ctx, len(ins[0]), *[_ptr(v) for v in ins], _ptr(ok)), "bjj_verify_batch")
         return ok
 
+    def verify_schnorr_batch(self, pkx, pky, msg, rx, ry, s):
+        ins = [_as_u8(v, 32) for v in (pkx, pky, msg, rx, ry, s)]
+        ok = np.empty(len(ins[0]), dtype=np.uint8)
+        status = np.empty(len(ins[0]), dtype=np.uint8)
+        self._check(self.lib.bjj_verify_schnorr_batch(self.ctx, len(ins[0]), *[_ptr(v) for v in ins], _ptr(ok), _ptr(status)),
+                    "bjj_verify_schnorr_batch")
+        return ok, status
+
     def verify_compressed_batch(self, sig64, pk32, msg):
         sg, pk, m = _as_u8(sig64, 64), _as_u8(pk32, 32), _as_u8(msg, 32)
         ok = np.empty(len(sg), dtype=np.uint8)
@@ -332,6 +340,26 @@ def verify(pk, sig, msg):
         raise ValueError("S wider than 256 bits")
     eng = default_engine()
     ok = eng.verify_batch(*[ints_to_le32([v]) for v in (sig.r_b8.x, sig.r_b8.y, sig.s, pk.x, pk.y, msg)])
+    return bool(ok[0])
+
+
+def schnorr_hash(pk, msg, c):
+    """src/lib.rs:364-373; raises ValueError("msg outside the Finite Field")."""
+    msg = int(msg)
+    if msg > Q:
+        raise ValueError(STATUS_STRINGS[4])
+    out = default_engine().poseidon_batch([ints_to_le32([v]) for v in (pk.x, pk.y, c.x, c.y, msg % Q)])
+    return le32_to_ints(out)[0]
+
+
+def verify_schnorr(pk, m, r, s):
+    """src/lib.rs:375-385.  `s` may be the reference's unreduced k + x*h: B8 has order SUBORDER, so it is
+    reduced on the host before crossing the 256-bit ABI."""
+    m = int(m)
+    ok, st = default_engine().verify_schnorr_batch(*[ints_to_le32([v]) for v in
+                                                    (pk.x, pk.y, m if m <= Q else (1 << 256) - 1, r.x, r.y, abs(int(s)) % SUBORDER)])
+    if st[0]:
+        raise ValueError(STATUS_STRINGS[int(st[0])])
     return bool(ok[0])
 
 

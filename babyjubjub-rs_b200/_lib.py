@@ -41,6 +41,7 @@ SIGNATURES = {
     "bjj_poseidon_batch": (_int, [_ctx, _int, _sz, ctypes.POINTER(_u8p), _u8p]),
     "bjj_verify_batch": (_int, [_ctx, _sz] + [_u8p] * 7),
     "bjj_verify_compressed_batch": (_int, [_ctx, _sz] + [_u8p] * 5),
+    "bjj_verify_schnorr_batch": (_int, [_ctx, _sz] + [_u8p] * 8),
 }
 # every batch op also has a device-pointer flavour with a trailing `void* stream`
 for _name in [k for k in SIGNATURES if k.endswith("_batch")]:

@@ -474,9 +474,10 @@ static int ensure_vscratch(bjj_ctx* ctx, Workspace* ws, size_t lanes, uint8_t** 
     return BJJ_OK;
 }
 
+// mode: BJJ_MODE_EDDSA (verify) or BJJ_MODE_SCHNORR (verify_schnorr; msg_status receives the per-lane Err)
 static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                          const uint8_t* ax, const uint8_t* ay, const uint8_t* msg, uint8_t* ok, cudaStream_t st,
-                         Workspace* ws) {
+                         Workspace* ws, int mode = BJJ_MODE_EDDSA, uint8_t* msg_status = nullptr) {
     for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
         const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
         const size_t o = 32 * off;
@@ -499,7 +500,8 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
             for (int e = 0; e < 4; e++) cudaEventCreate(&pe[e]);
             cudaEventRecord(pe[0], st);
         }
-        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, nullptr, hm, ok + off, true, qa, qr, ctx->flags_dev);
+        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, nullptr, hm, ok + off, true, qa, qr, ctx->flags_dev, mode,
+                          msg_status ? msg_status + off : nullptr);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         if (phase_timing) cudaEventRecord(pe[1], st);
@@ -507,11 +509,11 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         // (slow, rare) exact lanes follow on the side stream in single-warp CTAs that fit next to it.  All
         // three kernels write disjoint ok[] lanes.
         CU(ctx, cudaEventRecord(ws->ev_fork, st));
-        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, s + o, 1, 0, ax + o, ay + o, hm, ok + off, ws->table, ctx->comb);
+        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, s + o, 1, 0, ax + o, ay + o, hm, ok + off, ws->table, ctx->comb, mode);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
-        bjjk::verify_exact(ctx->sms * 8, ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr, ctx->comb);
+        bjjk::verify_exact(ctx->sms * 8, ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr, ctx->comb, mode);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
@@ -561,10 +563,11 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m, dax, day, status + off, 1);
         ctx->launches += 5;
         CU(ctx, cudaGetLastError());
-        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, q, ctx->flags_dev);
+        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, q, ctx->flags_dev, BJJ_MODE_EDDSA,
+                          nullptr);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        bjjk::verify_ec(grid_e, st, m, dx, dy, sig64 + 2 * o, 2, 1, dax, day, hm, ok + off, ws->table, ctx->comb);
+        bjjk::verify_ec(grid_e, st, m, dx, dy, sig64 + 2 * o, 2, 1, dax, day, hm, ok + off, ws->table, ctx->comb, BJJ_MODE_EDDSA);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
     }
@@ -667,6 +670,14 @@ int bjj_verify_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
     DEV_PROLOGUE
     if (!r8x || !r8y || !s32 || !ax || !ay || !msg32 || !ok) return BJJ_ERR_ARG;
     return launch_verify(ctx, n, r8x, r8y, s32, ax, ay, msg32, ok, st, &ctx->ws);
+}
+
+int bjj_verify_schnorr_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const uint8_t* pky, const uint8_t* msg32,
+                                 const uint8_t* rx, const uint8_t* ry, const uint8_t* s32, uint8_t* ok, uint8_t* status,
+                                 void* stream) {
+    DEV_PROLOGUE
+    if (!pkx || !pky || !msg32 || !rx || !ry || !s32 || !ok || !status) return BJJ_ERR_ARG;
+    return launch_verify(ctx, n, rx, ry, s32, pkx, pky, msg32, ok, st, &ctx->ws, BJJ_MODE_SCHNORR, status);
 }
 
 int bjj_verify_compressed_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
@@ -853,6 +864,16 @@ int bjj_verify_batch(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* 
     HostArg args[] = {H_IN(r8x, 32), H_IN(r8y, 32), H_IN(s32, 32), H_IN(ax, 32), H_IN(ay, 32), H_IN(msg32, 32), H_OUT(ok, 1)};
     return run_host(ctx, n, args, 7, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
         return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.ws);
+    });
+}
+
+int bjj_verify_schnorr_batch(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const uint8_t* pky, const uint8_t* msg32,
+                             const uint8_t* rx, const uint8_t* ry, const uint8_t* s32, uint8_t* ok, uint8_t* status) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(pkx, 32), H_IN(pky, 32), H_IN(msg32, 32), H_IN(rx, 32), H_IN(ry, 32), H_IN(s32, 32), H_OUT(ok, 1),
+                      H_OUT(status, 1)};
+    return run_host(ctx, n, args, 8, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+        return launch_verify(ctx, m, d[3], d[4], d[5], d[0], d[1], d[2], d[6], sl.stream, &sl.ws, BJJ_MODE_SCHNORR, d[7]);
     });
 }
 

@@ -24,9 +24,10 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
     size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                            const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
                                                            const uint8_t* skip, uint8_t* hm, uint8_t* ok, int gate,
-                                                           ExactQueue qa, ExactQueue qr, uint32_t* gflags) {
+                                                           ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode,
+                                                           uint8_t* msg_status) {
     BJJ_FLAGS_BEGIN
-    BJJ_LANE_LOOP(n) lane_verify_hash(r8x, r8y, ax, ay, msg, skip, hm, ok, i, gate != 0, qa, qr, flags);
+    BJJ_LANE_LOOP(n) lane_verify_hash(r8x, r8y, ax, ay, msg, skip, hm, ok, i, gate != 0, qa, qr, flags, mode, msg_status);
     BJJ_FLAGS_END(gflags)
 }
 
@@ -37,9 +38,9 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
 __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                          const uint8_t* s_base, size_t s_stride, size_t s_off,
                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
-                                                         uint8_t* ok, U128* table, const CombEntry* comb) {
+                                                         uint8_t* ok, U128* table, const CombEntry* comb, int mode) {
     const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, i, tbl, comb);
+    BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, i, tbl, comb, mode);
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
@@ -48,14 +49,14 @@ __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_verify_ec(size_t n, const uint
 __global__ void __launch_bounds__(BJJ_VERIFY_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                                          uint8_t* ok, ExactQueue qa, ExactQueue qr,
-                                                                         const CombEntry* comb) {
+                                                                         const CombEntry* comb, int mode) {
     const uint32_t half = gridDim.x / 2;
     if (blockIdx.x < half) {
         for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *qa.count; j < cnt; j += half * blockDim.x)
-            lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb);
+            lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb, mode);
     } else {
         for (uint32_t j = (blockIdx.x - half) * blockDim.x + threadIdx.x, cnt = *qr.count; j < cnt; j += half * blockDim.x)
-            lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb);
+            lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb, mode);
     }
 }
 
@@ -71,17 +72,18 @@ int verify_ec_blocks_per_sm() { return occ((const void*)k_verify_ec, BJJ_BLOCK);
 
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
-                 ExactQueue qa, ExactQueue qr, uint32_t* gflags) {
-    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, skip, hm, ok, gate ? 1 : 0, qa, qr, gflags);
+                 ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode, uint8_t* msg_status) {
+    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, skip, hm, ok, gate ? 1 : 0, qa, qr, gflags, mode, msg_status);
 }
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
                size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
-               U128* table, const CombEntry* comb) {
-    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, table, comb);
+               U128* table, const CombEntry* comb, int mode) {
+    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, table, comb, mode);
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
-                  const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb) {
-    k_verify_exact<<<grid & ~1, BJJ_VERIFY_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, hm, ok, qa, qr, comb);
+                  const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb,
+                  int mode) {
+    k_verify_exact<<<grid & ~1, BJJ_VERIFY_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, hm, ok, qa, qr, comb, mode);
 }
 
 }  // namespace bjjk

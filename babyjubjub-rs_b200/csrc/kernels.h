@@ -44,13 +44,13 @@ int poseidon_blocks_per_sm(int t);
 
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
-                 bjj::ExactQueue qa, bjj::ExactQueue qr, uint32_t* gflags);
+                 bjj::ExactQueue qa, bjj::ExactQueue qr, uint32_t* gflags, int mode, uint8_t* msg_status);
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
                size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
-               bjj::U128* table, const bjj::CombEntry* comb);
+               bjj::U128* table, const bjj::CombEntry* comb, int mode);
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, bjj::ExactQueue qa, bjj::ExactQueue qr,
-                  const bjj::CombEntry* comb);
+                  const bjj::CombEntry* comb, int mode);
 void mul_scalar(int grid, cudaStream_t st, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
                 bjj::ProjScratch scr, bjj::U128* table, bjj::ExactQueue q, uint32_t* gflags);
 void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx,

@@ -45,6 +45,7 @@ BJJ_HD void store_u256(uint8_t* base, size_t i, const uint32_t* w) {
 #define BJJ_ST_Y_RANGE 1      // "y outside the Finite Field over R"   src/lib.rs:202
 #define BJJ_ST_NO_INV 2       // "no mod inv of Zero"                  src/utils.rs:14
 #define BJJ_ST_NOT_SQUARE 3   // "not a mod p square"                  src/utils.rs:119
+#define BJJ_ST_MSG_RANGE 4    // "msg outside the Finite Field"        src/lib.rs:310, :366
 // batch-level flag bits (device word OR-ed by lanes)
 #define BJJ_FLAG_NONCANONICAL 1u   // a field-element input was >= Q (cannot happen through the Rust types)
 
@@ -685,7 +686,6 @@ BJJ_HD void mod_suborder(uint32_t* out, const uint32_t* x, int nwords) {
 // PrivateKey::sign (src/lib.rs:308-342).  status: 0 ok, 4 = "msg outside the Finite Field" (:310).
 //   h = BLAKE512(key); r = BLAKE512(h[32..64] || msg_le32) mod SUBORDER; R8 = B8*r; A = public();
 //   hm = Poseidon(R8.x, R8.y, A.x, A.y, msg);  S = (r + hm * (scalar_key << 3)) mod SUBORDER
-#define BJJ_ST_MSG_RANGE 4
 BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, const uint32_t* msg,
                           const CombEntry* comb, Fr& r8x_m, Fr& r8y_m) {
     const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
@@ -788,13 +788,24 @@ BJJ_HD void lane_sign(const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, 
 //   P = S*B8 + hm*(-8A)  and the test is  P == R8  checked projectively (no inversion).
 // Exact lane (any input point off the curve): the reference sequence replayed literally, in a second
 // kernel fed by the ExactQueue.
-BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& msg_m) {
+// mode selects the signature scheme sharing this pipeline:
+//   BJJ_MODE_EDDSA   verify          (src/lib.rs:395-412): hm = H(R8.x, R8.y, A.x, A.y, msg),  S*B8 == R8 + (8*hm)*A
+//   BJJ_MODE_SCHNORR verify_schnorr  (src/lib.rs:364-385): h  = H(pk.x, pk.y, r.x, r.y, msg),  s*B8 == r + h*pk
+// (`a` is the public key and `r8` the commitment point in both).
+#define BJJ_MODE_EDDSA 0
+#define BJJ_MODE_SCHNORR 1
+BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& msg_m, int mode) {
     Fr st[6];
     fr_zero(st[0]);
+    const bool sch = mode == BJJ_MODE_SCHNORR;
     st[1] = r8.x;
     st[2] = r8.y;
     st[3] = a.x;
     st[4] = a.y;
+    fr_cmov(st[1], a.x, sch);
+    fr_cmov(st[2], a.y, sch);
+    fr_cmov(st[3], r8.x, sch);
+    fr_cmov(st[4], r8.y, sch);
     st[5] = msg_m;
     poseidon_permute<6>(st);
     fr_from_mont(hm, st[0]);      // canonical integer hm < Q
@@ -802,12 +813,14 @@ BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& m
 
 // requires A and R8 ON the curve
 BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& hm,
-                            const LaneTable& tbl, const CombEntry* comb) {
+                            const LaneTable& tbl, const CombEntry* comb, int mode) {
     PointExt pa, acc;
     ext_from_affine(pa, a);
-    ext_dbl<false>(pa, pa);
-    ext_dbl<false>(pa, pa);
-    ext_dbl<true>(pa, pa);
+    if (mode == BJJ_MODE_EDDSA) {       // (8*hm)*A = hm*(8A); Schnorr multiplies pk by h itself
+        ext_dbl<false>(pa, pa);
+        ext_dbl<false>(pa, pa);
+        ext_dbl<true>(pa, pa);
+    }
     // negate: (-X, Y, Z, -T)
     fr_neg(pa.X, pa.X);
     fr_neg(pa.T, pa.T);
@@ -858,7 +871,7 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAf
 // The two cases are queued separately so a warp never executes both ladders.
 template <bool A_OFF>
 BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& hm,
-                             const CombEntry* comb) {
+                             const CombEntry* comb, int mode) {
     PointAff l, ka, ra;
     PointExt accl;
     PointProj pl;
@@ -867,17 +880,25 @@ BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointA
     if (A_OFF) {
         proj_affine(l, pl);
         uint32_t k9[9];
-        k9[0] = hm.v[0] << 3;
+        if (mode == BJJ_MODE_EDDSA) {
+            k9[0] = hm.v[0] << 3;
 #pragma unroll
-        for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
-        k9[8] = hm.v[7] >> 29;
+            for (int i = 1; i < 8; i++) k9[i] = (hm.v[i] << 3) | (hm.v[i - 1] >> 29);
+            k9[8] = hm.v[7] >> 29;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) k9[i] = hm.v[i];
+            k9[8] = 0;
+        }
         mul_scalar_exact(ka, a, k9, 9);
     } else {
         PointExt p8, acc;
         ext_from_affine(p8, a);
-        ext_dbl<false>(p8, p8);
-        ext_dbl<false>(p8, p8);
-        ext_dbl<true>(p8, p8);
+        if (mode == BJJ_MODE_EDDSA) {
+            ext_dbl<false>(p8, p8);
+            ext_dbl<false>(p8, p8);
+            ext_dbl<true>(p8, p8);
+        }
         Niels n8;
         niels_from_ext(n8, p8);
         ext_identity(acc);
@@ -920,7 +941,8 @@ BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointA
 #define BJJ_OK_PENDING 2
 BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
                              const uint8_t* msg32, const uint8_t* skip, uint8_t* hm_out, uint8_t* ok, size_t i,
-                             bool gate, const ExactQueue& qa, const ExactQueue& qr, uint32_t& flags) {
+                             bool gate, const ExactQueue& qa, const ExactQueue& qr, uint32_t& flags, int mode,
+                             uint8_t* msg_status) {
     if (skip && skip[i]) {
         ok[i] = 0;
         return;
@@ -928,7 +950,10 @@ BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8
     uint32_t msg[8];
     load_u256(msg, msg32, i);
     const uint32_t qq[8] = BJJ_LIMBS8(BJJ_Q);
-    if (u256_lt(qq, msg)) {     // msg > Q -> false; msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
+    const bool msg_bad = u256_lt(qq, msg);
+    // verify: msg > Q -> false (src/lib.rs:396); verify_schnorr: Err("msg outside the Finite Field") (:365-367)
+    if (msg_status) msg_status[i] = msg_bad ? (uint8_t)BJJ_ST_MSG_RANGE : (uint8_t)BJJ_ST_OK;
+    if (msg_bad) {     // msg == Q is accepted and hashed as 0 (src/lib.rs:396-399)
         ok[i] = 0;
         return;
     }
@@ -951,7 +976,7 @@ BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8
     Fr mraw, mm, hm;
     fr_set(mraw, msg);
     fr_to_mont(mm, mraw);
-    verify_hm(hm, r8, a, mm);
+    verify_hm(hm, r8, a, mm, mode);
     store_u256(hm_out, i, hm.v);
     ok[i] = (uint8_t)state;
 }
@@ -959,7 +984,7 @@ BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8
 // S of lane i sits at 32-byte element index i * s_stride + s_off (1, 0 for a plain S array; 2, 1 inside sig64)
 BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base, size_t s_stride,
                            size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm_in, uint8_t* ok,
-                           size_t i, const LaneTable& tbl, const CombEntry* comb) {
+                           size_t i, const LaneTable& tbl, const CombEntry* comb, int mode) {
     if (ok[i] != BJJ_OK_PENDING) return;
     uint32_t s[8], flags = 0;
     PointAff r8, a;
@@ -970,12 +995,13 @@ BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t
     load_fr(r8.y, r8y, i, flags);
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
-    ok[i] = (uint8_t)verify_fast(r8, s, a, hm, tbl, comb);
+    ok[i] = (uint8_t)verify_fast(r8, s, a, hm, tbl, comb, mode);
 }
 
 template <bool A_OFF>
 BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32, const uint8_t* ax,
-                              const uint8_t* ay, const uint8_t* hm_in, uint8_t* ok, size_t i, const CombEntry* comb) {
+                              const uint8_t* ay, const uint8_t* hm_in, uint8_t* ok, size_t i, const CombEntry* comb,
+                              int mode) {
     uint32_t s[8], flags = 0;
     PointAff r8, a;
     Fr hm;
@@ -985,7 +1011,7 @@ BJJ_HD void lane_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint
     load_fr(r8.y, r8y, i, flags);
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
-    ok[i] = (uint8_t)verify_exact<A_OFF>(r8, s, a, hm, comb);
+    ok[i] = (uint8_t)verify_exact<A_OFF>(r8, s, a, hm, comb, mode);
 }
 
 }  // namespace bjj

@@ -11,6 +11,7 @@
 //   Signature{r_b8,s}::compress            src/lib.rs:239-258
 //   PrivateKey{key}::scalar_key/public/sign src/lib.rs:270-342
 //   verify(pk, sig, msg)                   src/lib.rs:395-412
+//   verify_schnorr(pk, m, r, s)            src/lib.rs:375-385
 //   + batch entry points: mul_scalar_batch, public_batch, decompress_batch, verify_batch
 //   + MultiGpu: shards a batch over every device, one host thread + one bjj_ctx per device, no NCCL
 //
@@ -178,6 +179,17 @@ inline bool verify(const Point& pk, const Signature& sig, const U256& msg, Engin
     uint8_t ok = 0;
     Engine::check(bjj_verify_batch(e.ctx(), 1, sig.r_b8.x.data(), sig.r_b8.y.data(), sig.s.data(), pk.x.data(),
                                    pk.y.data(), msg.data(), &ok), "bjj_verify_batch");
+    return ok == 1;
+}
+
+// verify_schnorr (src/lib.rs:375-385): Result<bool, String> -- throws std::invalid_argument("msg outside the
+// Finite Field") for msg > Q.  `s` must already be reduced below 2^256 (the reference's s = k + x*h is an
+// unreduced ~1024-bit BigInt; reduce it mod SUBORDER, the order of B8).
+inline bool verify_schnorr(const Point& pk, const U256& m, const Point& r, const U256& s, Engine& e = default_engine()) {
+    uint8_t ok = 0, st = 0;
+    Engine::check(bjj_verify_schnorr_batch(e.ctx(), 1, pk.x.data(), pk.y.data(), m.data(), r.x.data(), r.y.data(), s.data(),
+                                           &ok, &st), "bjj_verify_schnorr_batch");
+    if (st) throw std::invalid_argument(bjj_status_string(st));
     return ok == 1;
 }
 

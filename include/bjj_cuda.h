@@ -54,7 +54,7 @@ typedef struct bjj_ctx bjj_ctx;
 #define BJJ_STATUS_Y_RANGE 1     /* "y outside the Finite Field over R"  src/lib.rs:202 */
 #define BJJ_STATUS_NO_INV 2      /* "no mod inv of Zero"                 src/utils.rs:14 */
 #define BJJ_STATUS_NOT_SQUARE 3  /* "not a mod p square"                 src/utils.rs:119 */
-#define BJJ_STATUS_MSG_RANGE 4   /* "msg outside the Finite Field"       src/lib.rs:310 (sign only) */
+#define BJJ_STATUS_MSG_RANGE 4   /* "msg outside the Finite Field"       src/lib.rs:310 sign, :366 schnorr */
 
 /* Fr test-hook opcodes (bjj_fr_op_batch) */
 #define BJJ_FR_MUL 0
@@ -146,6 +146,16 @@ int bjj_verify_batch(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* 
                      const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok);
 int bjj_verify_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32,
                          const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok, void* stream);
+
+/* ---- verify_schnorr (src/lib.rs:375-385) with schnorr_hash (src/lib.rs:364-373):
+ *      ok[i] = 1 iff s*B8 == r + h*pk, h = Poseidon(pk.x, pk.y, r.x, r.y, msg); status[i] = BJJ_STATUS_MSG_RANGE
+ *      (the reference's Err("msg outside the Finite Field")) when msg > Q.  s is 256-bit: the reference's s =
+ *      k + x*h is an unreduced ~1024-bit BigInt, which the host reduces mod SUBORDER (B8 has that order). ---- */
+int bjj_verify_schnorr_batch(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const uint8_t* pky, const uint8_t* msg32,
+                             const uint8_t* rx, const uint8_t* ry, const uint8_t* s32, uint8_t* ok, uint8_t* status);
+int bjj_verify_schnorr_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const uint8_t* pky, const uint8_t* msg32,
+                                 const uint8_t* rx, const uint8_t* ry, const uint8_t* s32, uint8_t* ok, uint8_t* status,
+                                 void* stream);
 
 /* ---- decompress_signature + decompress_point(pk) + verify (src/lib.rs:260-268, 192-224, 395-412):
  *      status[i] = first decompression error (R8 first, then A); ok[i] = 0 whenever status[i] != 0. -- */

@@ -300,6 +300,30 @@ def verify(pk, sig, msg):                               # src/lib.rs:395-412
     return l == proj_affine(r)
 
 
+# ---- Schnorr: src/lib.rs:344-385 ---------------------------------------------------------------
+def schnorr_hash(pk, msg, c):                           # src/lib.rs:364-373
+    if msg > Q:
+        raise ValueError("msg outside the Finite Field")
+    return poseidon([pk[0], pk[1], c[0], c[1], msg % Q])
+
+
+def sign_schnorr(key32, m, k):
+    """src/lib.rs:345-362 with the 1024-bit nonce `k` supplied by the caller (the reference draws it from
+    thread_rng, so there is no known-answer vector); s = k + scalar_key * h is NOT reduced."""
+    r = mul_scalar(B8, k)
+    pk = public(key32)
+    h = schnorr_hash(pk, m, r)
+    return r, k + scalar_key(key32) * h
+
+
+def verify_schnorr(pk, m, r, s):                        # src/lib.rs:375-385
+    sg = mul_scalar(B8, s)
+    h = schnorr_hash(pk, m, r)
+    pk_h = mul_scalar(pk, h)
+    right = proj_add((r[0], r[1], 1), (pk_h[0], pk_h[1], 1))
+    return sg == proj_affine(right)
+
+
 def compress_signature(sig):                            # src/lib.rs:245-257
     r8, s = sig
     return compress(r8) + (s & ((1 << 256) - 1)).to_bytes(32, "little")

@@ -59,6 +59,9 @@ extern "C" {
     // verify (src/lib.rs:395-412)
     pub fn bjj_verify_batch(ctx: *mut bjj_ctx, n: usize, r8x: *const u8, r8y: *const u8, s32: *const u8, ax: *const u8,
                             ay: *const u8, msg32: *const u8, ok: *mut u8) -> c_int;
+    // verify_schnorr + schnorr_hash (src/lib.rs:364-385)
+    pub fn bjj_verify_schnorr_batch(ctx: *mut bjj_ctx, n: usize, pkx: *const u8, pky: *const u8, msg32: *const u8,
+                                    rx: *const u8, ry: *const u8, s32: *const u8, ok: *mut u8, status: *mut u8) -> c_int;
     // decompress_signature + decompress_point + verify (src/lib.rs:260-268)
     pub fn bjj_verify_compressed_batch(ctx: *mut bjj_ctx, n: usize, sig64: *const u8, pk32: *const u8,
                                        msg32: *const u8, ok: *mut u8, status: *mut u8) -> c_int;

@@ -134,12 +134,17 @@ class _CBackend:
         outs, _ = self._call(self.names["verify_compressed"], n, [_c(sig64, 64), pk32, msg], [(n,), (n,)])
         return outs
 
+    def verify_schnorr(self, pkx, pky, msg, rx, ry, s):
+        n = len(pkx)
+        outs, _ = self._call(self.names["verify_schnorr"], n, [pkx, pky, msg, rx, ry, s], [(n,), (n,)])
+        return outs
+
 
 class OracleC(_CBackend):
     prefix = "ora_"
     has_threads = True
     names = {k: k + "_batch" for k in ("add", "affine", "mul_scalar", "fixed_base", "public", "scalar_key", "compress",
-                                       "decompress", "verify", "verify_compressed")}
+                                       "decompress", "verify", "verify_compressed", "verify_schnorr")}
 
     def __init__(self, threads=None):
         self.lib = ctypes.CDLL(build_oracle_c())
@@ -175,7 +180,7 @@ class HostEmu(_CBackend):
     prefix = "emu_"
     has_threads = False
     names = {k: k for k in ("add", "affine", "mul_scalar", "fixed_base", "public", "scalar_key", "compress",
-                            "decompress", "verify", "verify_compressed")}
+                            "decompress", "verify", "verify_compressed", "verify_schnorr")}
 
     def __init__(self):
         self.lib = ctypes.CDLL(build_hostemu())
@@ -243,6 +248,9 @@ class Gpu:
 
     def verify_compressed(self, sig64, pk32, msg):
         return list(self.eng.verify_compressed_batch(sig64, pk32, msg))
+
+    def verify_schnorr(self, pkx, pky, msg, rx, ry, s):
+        return list(self.eng.verify_schnorr_batch(pkx, pky, msg, rx, ry, s))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -181,10 +181,24 @@ uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint
     uint32_t flags = 0;
     ExactQueue qa = exact_queue(n), qr = exact_queue2(n);
     std::vector<uint8_t> hm(32 * (n + 1));
-    for (size_t i = 0; i < n; i++) lane_verify_hash(r8x, r8y, ax, ay, msg, nullptr, hm.data(), ok, i, true, qa, qr, flags);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, s, 1, 0, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
-    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list[j], g_comb);
-    for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list2[j], g_comb);
+    for (size_t i = 0; i < n; i++) lane_verify_hash(r8x, r8y, ax, ay, msg, nullptr, hm.data(), ok, i, true, qa, qr, flags, BJJ_MODE_EDDSA, nullptr);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, s, 1, 0, ax, ay, hm.data(), ok, i, lane_table(), g_comb, BJJ_MODE_EDDSA);
+    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list[j], g_comb, BJJ_MODE_EDDSA);
+    for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list2[j], g_comb, BJJ_MODE_EDDSA);
+    return flags;
+}
+
+uint32_t emu_verify_schnorr(size_t n, const uint8_t* pkx, const uint8_t* pky, const uint8_t* msg, const uint8_t* rx,
+                            const uint8_t* ry, const uint8_t* s, uint8_t* ok, uint8_t* status) {
+    emu_init();
+    uint32_t flags = 0;
+    ExactQueue qa = exact_queue(n), qr = exact_queue2(n);
+    std::vector<uint8_t> hm(32 * (n + 1));
+    for (size_t i = 0; i < n; i++)
+        lane_verify_hash(rx, ry, pkx, pky, msg, nullptr, hm.data(), ok, i, true, qa, qr, flags, BJJ_MODE_SCHNORR, status);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(rx, ry, s, 1, 0, pkx, pky, hm.data(), ok, i, lane_table(), g_comb, BJJ_MODE_SCHNORR);
+    for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(rx, ry, s, pkx, pky, hm.data(), ok, g_list[j], g_comb, BJJ_MODE_SCHNORR);
+    for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(rx, ry, s, pkx, pky, hm.data(), ok, g_list2[j], g_comb, BJJ_MODE_SCHNORR);
     return flags;
 }
 
@@ -201,8 +215,8 @@ void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, 
     batch_inverse(scr, 2 * n);
     for (size_t i = 0; i < n; i++) lane_decompress_finish(sig64, 2, 0, scr, i, dx, dy, status, i, false);
     for (size_t i = 0; i < n; i++) lane_decompress_finish(pk32, 1, 0, scr, n + i, ax, ay, status, i, true);
-    for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, q, flags);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, sig64, 2, 1, ax, ay, hm.data(), ok, i, lane_table(), g_comb);
+    for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, q, flags, BJJ_MODE_EDDSA, nullptr);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, sig64, 2, 1, ax, ay, hm.data(), ok, i, lane_table(), g_comb, BJJ_MODE_EDDSA);
 }
 
 }  // extern "C"

@@ -180,3 +180,52 @@ def check_sign(be, ref, n_random, seed=8):
     ax, ay = be.public(K[ok])
     v = be.verify(got[0][ok], got[1][ok], got[2][ok], ax, ay, M[ok])
     assert v.all()
+
+
+def check_schnorr(be, ref, n_valid, seed=9):
+    """verify_schnorr / schnorr_hash (src/lib.rs:364-385): round trips as in the reference's
+    test_schnorr_signature (:677-686, random nonce, so no KAT) plus the negative and off-curve cases"""
+    rnd = random.Random(seed)
+    on, off = special_points()
+    cases = []          # [pkx, pky, msg, rx, ry, s (reduced mod SUBORDER for the 256-bit ABI)]
+    full = []           # the same with the reference's unreduced s, for the Python oracle
+    for _ in range(n_valid):
+        key, m, k = rnd.randbytes(32), rnd.randrange(Q), rnd.getrandbits(1024)
+        r, s = O.sign_schnorr(key, m, k)
+        pk = O.public(key)
+        full.append((pk, m, r, s))
+        cases.append([pk[0], pk[1], m, r[0], r[1], s % O.SUBORDER])
+    base, bfull = cases[0], full[0]
+    def mod(i, v):
+        c = list(base)
+        c[i] = v
+        return c
+    cases.append(mod(5, base[5] ^ 1))                           # wrong s
+    cases.append(mod(2, base[2] ^ 4))                           # wrong msg
+    cases.append(mod(5, base[5] + O.SUBORDER))                  # s + SUBORDER: still valid
+    cases.append(mod(2, Q + 1))                                 # Err: msg outside the field
+    cases.append(mod(2, (1 << 256) - 1))
+    cases.append(mod(0, (base[0] + 1) % Q))                     # off-curve pk  -> literal ladder
+    cases.append(mod(3, (base[3] + 1) % Q))                     # off-curve r   -> literal final add
+    c = list(base); c[0], c[1] = 0, 0; cases.append(c)
+    c = list(base); c[3], c[4] = 0, 0; cases.append(c)
+    c = list(base); c[0], c[1] = cases[1][0], cases[1][1]; cases.append(c)      # foreign pk
+    s0 = rnd.randrange(O.SUBORDER)
+    R = O.mul_scalar(O.B8, s0)
+    cases.append([0, 1, 5, R[0], R[1], s0])                     # pk = identity: s*B8 == r
+    arrs = cases_to_arrays(cases)
+    gok, gst = be.verify_schnorr(*arrs)
+    eok, est = ref.verify_schnorr(*arrs)
+    _eq(gst, est, "verify_schnorr status")
+    _eq(gok, eok, "verify_schnorr ok")
+    assert list(gok[:n_valid]) == [1] * n_valid and 0 in gok and 4 in gst
+    # the checker against the Python oracle, with the reference's unreduced s for the valid ones
+    for i, (pk, m, r, s) in enumerate(full):
+        assert O.verify_schnorr(pk, m, r, s) is True and gok[i] == 1
+    for i in range(n_valid, len(cases)):
+        c = cases[i]
+        try:
+            e, st = int(O.verify_schnorr((c[0], c[1]), c[2], (c[3], c[4]), c[5])), 0
+        except ValueError:
+            e, st = 0, 4
+        assert (gok[i], gst[i]) == (e, st), i

@@ -247,3 +247,54 @@ def test_verify_random_corruption_mix_vs_oracle(gpu, oracle_c):
     gok, gst = gpu.verify_compressed(sig64, pk32, cols[5])
     eok, est = oracle_c.verify_compressed(sig64, pk32, cols[5])
     assert np.array_equal(gst, est) and np.array_equal(gok, eok)
+
+
+def test_abi_argument_errors_and_context_lifecycle(gpu):
+    """C-ABI error behaviour: null pointers / bad counts are BJJ_ERR_ARG, contexts are independent and can be
+    created, used from their own host threads, and destroyed repeatedly"""
+    import ctypes
+    import threading
+    bjj = gpu.bjj
+    lib = gpu.eng.lib
+    ctx = gpu.eng.ctx
+    buf = pack([1, 2, 3])
+    p = buf.ctypes.data_as(ctypes.c_void_p)
+    assert lib.bjj_fixed_base_batch(ctx, 3, None, p, p) == 2                       # BJJ_ERR_ARG
+    assert lib.bjj_fr_op_batch(ctx, 9, 3, p, p, p) == 2
+    assert lib.bjj_poseidon_batch(ctx, 0, 3, (ctypes.c_void_p * 1)(p), p) == 2
+    assert lib.bjj_poseidon_batch(ctx, 9, 3, (ctypes.c_void_p * 1)(p), p) == 2
+    assert lib.bjj_verify_batch(None, 3, p, p, p, p, p, p, p) == 2
+    assert lib.bjj_fixed_base_batch(ctx, 0, p, p, p) == 0                          # empty batch is fine
+    assert lib.bjj_status_string(3) == b"not a mod p square"
+    assert lib.bjj_status_string(1) == b"y outside the Finite Field over R"
+    assert lib.bjj_status_string(4) == b"msg outside the Finite Field"
+    assert lib.bjj_error_string(3).startswith(b"field element input >= Q")
+    assert lib.bjj_device(ctx) == 0 and lib.bjj_stream(ctx)
+    before = gpu.eng.kernel_launches
+    gpu.eng.fixed_base_batch(pack([5]))
+    assert gpu.eng.kernel_launches == before + 2                                   # comb kernel + batched affine
+    # two more contexts on the same device, each driven by its own host thread
+    k = pack([(i * 0x9E3779B97F4A7C15 + 7) % (1 << 256) for i in range(3000)])
+    ref = gpu.eng.fixed_base_batch(k)
+    out = {}
+
+    def work(tag):
+        e = bjj.Engine(0)
+        for _ in range(3):
+            out[tag] = e.fixed_base_batch(k)
+        e.close()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for tag in range(2):
+        assert np.array_equal(out[tag][0], ref[0]) and np.array_equal(out[tag][1], ref[1])
+    for _ in range(3):                                                              # create / destroy repeatedly
+        e = bjj.Engine(0)
+        assert unpack(e.fr_op_batch(bjj.FR_ADD, pack([Q - 1]), pack([2])))[0] == 1
+        e.close()
+
+
+def test_schnorr(gpu, oracle_c):
+    parity.check_schnorr(gpu, oracle_c, 64)

@@ -33,3 +33,7 @@ def test_verify(hostemu, oracle_c):
 
 def test_sign(hostemu, oracle_c):
     parity.check_sign(hostemu, oracle_c, 6)
+
+
+def test_schnorr(hostemu, oracle_c):
+    parity.check_schnorr(hostemu, oracle_c, 3)

@@ -92,3 +92,4 @@ def test_c_oracle_matches_python_oracle(oracle_c):
     parity.check_compress_decompress(oracle_c, oracle_c, 40)
     parity.check_poseidon(oracle_c, oracle_c, 4)
     parity.check_verify(oracle_c, oracle_c, 2)
+    parity.check_schnorr(oracle_c, oracle_c, 2)
