@@ -278,7 +278,7 @@ BJJ_HD void fr_merge_xy(Fr& r, const uint32_t* X, const uint32_t* Y) {
 }
 
 // r = a * b / 2^256 mod Q;  a, b in [0, 2Q)  ->  r in [0, 2Q)   (also valid for a < 2^256, b < Q)
-BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) {
+BJJ_HD void fr_mul_inline(Fr& r, const Fr& a, const Fr& b) {
     uint32_t X[18], Y[18];
 #pragma unroll
     for (int i = 0; i < 18; i++) X[i] = Y[i] = 0;
@@ -292,6 +292,10 @@ BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) {
     BJJ_MUL_STEP(Y, X, 7, true)
     fr_merge_xy(r, X, Y);
 }
+
+// (An out-of-line multiplier -- one copy per kernel, 50x less code -- was measured and rejected: 22.5 vs
+// 26.1 M mults/s in k_mul_scalar; inlining lets ptxas interleave independent multiplications.)
+BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) { fr_mul_inline(r, a, b); }
 
 // One step of a Montgomery dot product  sum_p A_p * B_p  at column I (see fr_dot).
 #define BJJ_DOT_STEP(S, N, I, FOLD)                                                                   \
