@@ -498,6 +498,59 @@ def run_secondaries(args, eng, torch, dev, stream, common):
     assert np.array_equal(ok[idx].cpu().numpy(), eok) and np.array_equal(stt[idx].cpu().numpy(), est), "verify_compressed parity"
     out.append({"metric": "compressed_pipeline_verifies_per_sec", "workload": "verify_compressed_batch: 2^19 x (64 B sig + 32 B pk + 32 B msg) per GPU (config 5)",
                 "value": n / (ms * 1e-3), "unit": "verifies/s", "ms_per_step": ms, "oracle_checked_lanes": 2048})
+    # the remaining rows of the hot-path table, each with its own bound ------------------------------------------
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n = 1 << 20
+    # decompress_point (row a7): 2^20 compressed points, ~345 fmul each -> IMAD-bound
+    comp2 = torch.cat([comp_a, comp_r], dim=0).contiguous()          # 2^20 valid compressed points
+    st2 = torch.empty(n, dtype=torch.uint8, device=dev)
+    dx, dy = (torch.empty((n, 32), dtype=torch.uint8, device=dev) for _ in range(2))
+    ms = timed(lambda: lib.bjj_decompress_batch_dev(ctx, n, dptr(comp2), dptr(dx), dptr(dy), dptr(st2), sp), args.steps)
+    ex, ey, est = ora.decompress(comp2[:1024].cpu().numpy())
+    assert np.array_equal(dx[:1024].cpu().numpy(), ex) and np.array_equal(st2[:1024].cpu().numpy(), est), "decompress_batch parity"
+    rate = n / (ms * 1e-3)
+    out.append({"metric": "decompress_points_per_sec", "workload": "decompress_batch: 2^20 compressed points", "value": rate,
+                "unit": "points/s", "ms_per_step": ms, "roofline_frac_imad": rate * 345 * FMUL / imad_peak, "oracle_checked_lanes": 1024})
+    # POSEIDON.hash with 5 inputs (row a8)
+    ins = [dx, dy, r8x.repeat(2, 1)[:n].contiguous(), r8y.repeat(2, 1)[:n].contiguous(), msgs.repeat(2, 1)[:n].contiguous()]
+    arr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ins])
+    ho = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.bjj_poseidon_batch_dev(ctx, 5, n, arr, dptr(ho), sp), args.steps)
+    eh = ora.poseidon([t[:256].cpu().numpy() for t in ins])
+    assert np.array_equal(ho[:256].cpu().numpy(), eh), "poseidon_batch parity"
+    rate = n / (ms * 1e-3)
+    out.append({"metric": "poseidon5_hashes_per_sec", "workload": "poseidon_batch: 2^20 x 5 inputs (t = 6)", "value": rate,
+                "unit": "hashes/s", "ms_per_step": ms, "roofline_frac_imad": rate * (POSEIDON6_MAC + 6 * FMUL) / imad_peak,
+                "oracle_checked_lanes": 256})
+    # Point::compress (row a6): pure data movement, 64 B in + 32 B out per point -> HBM-bound
+    n = 1 << 22
+    bx = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    by = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    bx[:, 31] &= 0x0F
+    by[:, 31] &= 0x0F
+    bo = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.bjj_compress_batch_dev(ctx, n, dptr(bx), dptr(by), dptr(bo), sp), args.steps * 4)
+    assert np.array_equal(bo[:4096].cpu().numpy(), ora.compress(bx[:4096].cpu().numpy(), by[:4096].cpu().numpy())), "compress parity"
+    gbs = n * 96 / (ms * 1e-3) / 1e9
+    out.append({"metric": "compress_points_per_sec", "workload": "compress_batch: 2^22 points (403 MB per step, larger than L2)",
+                "value": n / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak},
+                "oracle_checked_lanes": 4096})
+    # PointProjective::add (row a2): 6 x 32 B in, 3 x 32 B out, 13 fmul (+9 Montgomery conversions)
+    n = 1 << 21
+    one = torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+    one[:, 0] = 1
+    px2, py2 = bx[:n].contiguous(), by[:n].contiguous()
+    qx2, qy2 = bx[n:2 * n].contiguous(), by[n:2 * n].contiguous()
+    o3 = [torch.empty((n, 32), dtype=torch.uint8, device=dev) for _ in range(3)]
+    ms = timed(lambda: lib.bjj_add_batch_dev(ctx, n, dptr(px2), dptr(py2), dptr(one), dptr(qx2), dptr(qy2), dptr(one),
+                                             dptr(o3[0]), dptr(o3[1]), dptr(o3[2]), sp), args.steps * 2)
+    ea = ora.add(*[t[:1024].cpu().numpy() for t in (px2, py2, one, qx2, qy2, one)])
+    assert all(np.array_equal(o3[k][:1024].cpu().numpy(), ea[k]) for k in range(3)), "add_batch parity"
+    rate = n / (ms * 1e-3)
+    out.append({"metric": "projective_adds_per_sec", "workload": "add_batch: 2^21 projective pairs (literal add-2008-bbjlp)",
+                "value": rate, "unit": "adds/s", "ms_per_step": ms, "roofline_frac_imad": rate * 22 * FMUL / imad_peak,
+                "hbm_frac": rate * 288 / 1e9 / hbm_peak, "oracle_checked_lanes": 1024})
     return out
 
 
