@@ -21,10 +21,9 @@ using namespace bjj;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BJJ_BLOCK) k_comb_build(CombEntry* comb) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES) return;
-    int w = idx / BJJ_COMB_ENTRIES, j = idx % BJJ_COMB_ENTRIES;
-    if (w == 32 && j > 1) return;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= BJJ_COMB_TOTAL) return;
+    int w = (int)(idx / BJJ_COMB_ENTRIES), j = (int)(idx % BJJ_COMB_ENTRIES);
     comb_build_entry(comb, w, j);
 }
 
@@ -348,10 +347,10 @@ int bjj_init(int device, bjj_ctx** out) {
     INIT_CU(cudaMalloc(&ctx->flags_dev, sizeof(uint32_t)));
     INIT_CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(uint32_t), ctx->stream));
     INIT_CU(cudaHostAlloc(&ctx->flags_host, sizeof(uint32_t), cudaHostAllocDefault));
-    const size_t comb_bytes = (size_t)BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES * sizeof(CombEntry);
+    const size_t comb_bytes = BJJ_COMB_TOTAL * sizeof(CombEntry);
     INIT_CU(cudaMalloc(&ctx->comb, comb_bytes));
     INIT_CU(cudaMemsetAsync(ctx->comb, 0, comb_bytes, ctx->stream));
-    const int total = BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES;
+    const size_t total = BJJ_COMB_TOTAL;
     k_comb_build<<<(total + BJJ_BLOCK - 1) / BJJ_BLOCK, BJJ_BLOCK, 0, ctx->stream>>>(ctx->comb);
     ctx->launches++;
     INIT_CU(cudaGetLastError());

@@ -131,10 +131,19 @@ BJJ_HD void table_select(Niels& n, const LaneTable& t, int d) {
 }
 
 // ---- fixed-base comb for B8 ------------------------------------------------------------------------
-// comb[w][j] = j * 256^w * B8 as affine Niels (y+x, y-x, 2d'xy) on the a = -1 model, j = 0..128,
-// w = 0..32 (w = 32 only holds j = 0, 1 for the recoding carry).  Built once per context on the device.
-#define BJJ_COMB_WINDOWS 33
-#define BJJ_COMB_ENTRIES 129
+// comb[w][j] = j * 65536^w * B8 as affine Niels (y+x, y-x, 2d'xy) on the a = -1 model, j = 0..32768,
+// w = 0..16 (w = 16 only holds j = 0, 1 for the recoding carry): 16 x 32,769 x 96 B = 50 MB, L2-resident,
+// gathered with ld.global.nc.  Built once per context on the device (k_comb_build, ~15 ms).  Signed 16-bit
+// digits make a fixed-base multiplication 17 mixed additions and no doubling; the Straus pass of verify
+// reads window 0 of the same table every fourth radix-16 window.
+#define BJJ_COMB_BITS 16
+#define BJJ_COMB_WINDOWS 17
+#define BJJ_COMB_ENTRIES 32769
+#define BJJ_COMB_TOTAL ((size_t)(BJJ_COMB_WINDOWS - 1) * BJJ_COMB_ENTRIES + 2)
+#if !BJJ_DEVICE_CODE && defined(BJJ_HOST_EMU)
+// the host test harness fills table entries on demand instead of building all 524,290 of them
+void bjj_hostemu_need_entry(const struct CombEntry* comb, int w, int j);
+#endif
 struct CombEntry {   // 96 bytes
     uint32_t ypx[8], ymx[8], t2d[8];
 };
@@ -142,6 +151,9 @@ struct CombEntry {   // 96 bytes
 BJJ_HD void comb_select(NielsAff& n, const CombEntry* comb, int w, int d) {
     int ad = d < 0 ? -d : d;
     const CombEntry* e = comb + (size_t)w * BJJ_COMB_ENTRIES + ad;
+#if !BJJ_DEVICE_CODE && defined(BJJ_HOST_EMU)
+    bjj_hostemu_need_entry(comb, w, ad);
+#endif
 #if BJJ_DEVICE_CODE
     const uint4* p = reinterpret_cast<const uint4*>(e);
     uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4), q5 = __ldg(p + 5);
@@ -159,22 +171,22 @@ BJJ_HD void comb_select(NielsAff& n, const CombEntry* comb, int w, int d) {
     niels_aff_cneg(n, d < 0);
 }
 
-// acc = k * B8 for a 256-bit k: 33 mixed additions, no doublings.
+// acc = k * B8 for a 256-bit k: 17 mixed additions, no doublings.
 BJJ_HD void fixed_base_comb(PointExt& acc, const CombEntry* comb, const uint32_t* k) {
-    Recode8 rc;
-    recode8(rc, k);
+    Recode16 rc;
+    recode16(rc, k);
     ext_identity(acc);
     NielsAff n;
-    comb_select(n, comb, 32, (int)rc.top);
+    comb_select(n, comb, BJJ_COMB_WINDOWS - 1, (int)rc.top);
     ext_add_niels_aff<true>(acc, acc, n);
 #pragma unroll 1
-    for (int w = 31; w >= 0; w--) {
-        comb_select(n, comb, w, recode8_digit(rc, w));
+    for (int w = BJJ_COMB_WINDOWS - 2; w >= 0; w--) {
+        comb_select(n, comb, w, recode16_digit(rc, w));
         ext_add_niels_aff<true>(acc, acc, n);
     }
 }
 
-// one comb entry: j * 256^w * B8   (init kernel; one thread per (w, j))
+// one comb entry: j * 65536^w * B8   (init kernel; one thread per (w, j))
 BJJ_HD void comb_build_entry(CombEntry* comb, int w, int j) {
     CombEntry* e = comb + (size_t)w * BJJ_COMB_ENTRIES + j;
     PointAff b8;
@@ -183,12 +195,12 @@ BJJ_HD void comb_build_entry(CombEntry* comb, int w, int j) {
     PointExt base, acc;
     ext_from_affine(base, b8);
 #pragma unroll 1
-    for (int i = 0; i < 8 * w; i++) ext_dbl<true>(base, base);
+    for (int i = 0; i < BJJ_COMB_BITS * w; i++) ext_dbl<true>(base, base);
     ext_identity(acc);
     Niels nb;
     niels_from_ext(nb, base);
 #pragma unroll 1
-    for (int bit = 7; bit >= 0; bit--) {
+    for (int bit = BJJ_COMB_BITS - 1; bit >= 0; bit--) {
         ext_dbl<true>(acc, acc);
         if ((j >> bit) & 1) ext_add_niels<true>(acc, acc, nb);
     }
@@ -827,8 +839,8 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAf
     table_build(tbl, pa);
     Recode4 ra;
     recode4(ra, hm.v);
-    Recode8 rs;
-    recode8(rs, s);
+    Recode16 rs;
+    recode16(rs, s);
     ext_identity(acc);
     Niels nn;
     NielsAff nb;
@@ -843,11 +855,11 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAf
         ext_dbl<false>(acc, acc);
         ext_dbl<true>(acc, acc);
         table_select(nn, tbl, recode4_digit(ra, i));
-        if (i & 1) {
+        if (i & 3) {
             ext_add_niels<false>(acc, acc, nn);
-        } else {
+        } else {      // every fourth radix-16 window: one 16-bit digit of S against the B8 table
             ext_add_niels<true>(acc, acc, nn);
-            comb_select(nb, comb, 0, recode8_digit(rs, i >> 1));
+            comb_select(nb, comb, 0, recode16_digit(rs, i >> 2));
             ext_add_niels_aff<false>(acc, acc, nb);
         }
     }

@@ -42,9 +42,9 @@ UNIT = "verifies/s"
 FMUL = 128
 ALGO_FMUL = {
     # gates 10 + Montgomery conversions 10 + map 2 + 8A 22 + table 64 + first adds 15
-    # + 32 x (2 x (3 x 7 + 8) + 7 + 8 + 6) Straus windows + projective compare 3
-    "verify_ec": 10 + 10 + 2 + 22 + 64 + 15 + 32 * (2 * 29 + 21) + 3,
-    "fixed_base": 33 * 7 + 1 + 5 + 2 + 12,            # comb + map + batched inversion share
+    # + 16 x (4 x (3 x 7 + 8) + 3 x 7 + 8 + 6) Straus windows (one 16-bit B8 digit per 4 nibbles of hm) + compare 3
+    "verify_ec": 10 + 10 + 2 + 22 + 64 + 15 + 16 * (4 * 29 + 35) + 3,
+    "fixed_base": 17 * 7 + 1 + 5 + 2 + 12,            # 16-bit comb + map + batched inversion share
     "mul_scalar": 2 + 5 + 2 + 64 + 7 + 64 * 36 + 20,  # gate, table, 64 windows x (4 dbl + add), batched inversion share
 }
 # Poseidon t = 6, sparse schedule: 8 full rounds x (6 x^5 + 6 dot6) + 60 partial x (x^5 + dot6 + 5 fmul)

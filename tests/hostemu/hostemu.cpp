@@ -13,6 +13,17 @@
 using namespace bjj;
 
 static CombEntry* g_comb = nullptr;
+static uint8_t* g_comb_valid = nullptr;
+
+// comb entries are built on demand (the device builds all 524,290 in k_comb_build; here a test touches a few)
+namespace bjj {
+void bjj_hostemu_need_entry(const CombEntry* comb, int w, int j) {
+    const size_t idx = (size_t)w * BJJ_COMB_ENTRIES + j;
+    if (comb != g_comb || g_comb_valid[idx]) return;
+    g_comb_valid[idx] = 1;
+    comb_build_entry(g_comb, w, j);
+}
+}  // namespace bjj
 static std::vector<U128> g_table(BJJ_TABLE_U128_PER_LANE);
 
 static std::vector<uint32_t> g_list, g_list2;
@@ -62,12 +73,8 @@ extern "C" {
 
 void emu_init() {
     if (g_comb) return;
-    g_comb = (CombEntry*)calloc((size_t)BJJ_COMB_WINDOWS * BJJ_COMB_ENTRIES, sizeof(CombEntry));
-    for (int w = 0; w < BJJ_COMB_WINDOWS; w++)
-        for (int j = 0; j < BJJ_COMB_ENTRIES; j++) {
-            if (w == 32 && j > 1) continue;
-            comb_build_entry(g_comb, w, j);
-        }
+    g_comb = (CombEntry*)calloc(BJJ_COMB_TOTAL, sizeof(CombEntry));     // pages are committed on first touch
+    g_comb_valid = (uint8_t*)calloc(BJJ_COMB_TOTAL, 1);
 }
 
 uint32_t emu_fr_op(int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
