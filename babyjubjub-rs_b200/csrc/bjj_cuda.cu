@@ -103,7 +103,7 @@ struct Workspace {
     size_t exact_cap;
     uint8_t* proj;           // 4 x 32 B per lane: X, Y, Z, running product
     size_t proj_lanes;
-    uint8_t* vs;             // verify scratch: hm + decompressed R8, A (5 x 32 B per lane)
+    uint8_t* vs;             // verify scratch: hm, u, v, w + decompressed R8, A (8 x 32 B per lane)
     size_t vs_lanes;
     cudaStream_t aux;        // side stream: the exact-lane kernel overlaps the fast EC kernel
     cudaEvent_t ev_fork, ev_join;
@@ -127,6 +127,7 @@ struct bjj_ctx {
     PipeSlot slot[BJJ_PIPE_SLOTS];
     unsigned long long launches;
     cudaError_t last;
+    bool verify_split;          // half-size scalars in verify (split.cuh); BJJ_VERIFY_SPLIT=0 turns it off
 };
 
 #define CU(ctx, call)                      \
@@ -329,6 +330,10 @@ int bjj_init(int device, bjj_ctx** out) {
     if (!ctx) return BJJ_ERR_NOMEM;
     ctx->device = device;
     ctx->last = cudaSuccess;
+    {
+        const char* e = getenv("BJJ_VERIFY_SPLIT");
+        ctx->verify_split = !(e && e[0] == '0');
+    }
 #define INIT_CU(call)                  \
     do {                               \
         cudaError_t e_ = (call);       \
@@ -459,17 +464,18 @@ static int launch_decompress(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_
     return BJJ_OK;
 }
 
-// verify scratch: hm (32 B / lane) and, for the compressed pipeline, the four decompressed coordinates
+// verify scratch: four planes hm | u | v | w (32 B / lane each; u, v, w are the Straus scalars, see split.cuh)
+// and, for the compressed pipeline, the four decompressed coordinates
 static int ensure_vscratch(bjj_ctx* ctx, Workspace* ws, size_t lanes, uint8_t** hm, uint8_t** pts) {
     if (ws->vs_lanes < lanes) {
         if (ws->vs) cudaFree(ws->vs);
         ws->vs = nullptr;
         ws->vs_lanes = 0;
-        CU(ctx, cudaMalloc(&ws->vs, lanes * 160));
+        CU(ctx, cudaMalloc(&ws->vs, lanes * 256));
         ws->vs_lanes = lanes;
     }
     *hm = ws->vs;
-    *pts = ws->vs + 32 * ws->vs_lanes;
+    *pts = ws->vs + 4 * 32 * ws->vs_lanes;
     return BJJ_OK;
 }
 
@@ -482,7 +488,7 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         const size_t o = 32 * off;
         const int grid_h = grid_cap(ctx, bjjk::verify_hash_blocks_per_sm(), m);
         const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
-        int rc = ensure_table(ctx, ws, (size_t)grid_e * BJJ_BLOCK);
+        int rc = ensure_table(ctx, ws, 2 * (size_t)grid_e * BJJ_BLOCK);     // two per-thread tables: 8A and R8
         if (rc) return rc;
         ExactQueue qa, qr;
         rc = ensure_queue(ctx, ws, m, st, &qa, &qr);
@@ -499,16 +505,21 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
             for (int e = 0; e < 4; e++) cudaEventCreate(&pe[e]);
             cudaEventRecord(pe[0], st);
         }
-        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, nullptr, hm, ok + off, true, qa, qr, ctx->flags_dev, mode,
-                          msg_status ? msg_status + off : nullptr);
+        bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, s + o, 1, 0, nullptr, hm, ws->vs_lanes, ok + off, true,
+                          qa, qr, ctx->flags_dev, mode, ctx->verify_split, msg_status ? msg_status + off : nullptr);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
+        if (ctx->verify_split && mode == BJJ_MODE_EDDSA) {
+            bjjk::verify_split(grid_cap(ctx, bjjk::verify_split_blocks_per_sm(), m), st, m, s + o, 1, 0, hm, ws->vs_lanes, ok + off);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+        }
         if (phase_timing) cudaEventRecord(pe[1], st);
         // the queues are complete.  The Straus kernel goes first so that its CTAs are placed first; the
         // (slow, rare) exact lanes follow on the side stream in single-warp CTAs that fit next to it.  All
         // three kernels write disjoint ok[] lanes.
         CU(ctx, cudaEventRecord(ws->ev_fork, st));
-        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, s + o, 1, 0, ax + o, ay + o, hm, ok + off, ws->table, ctx->comb, mode);
+        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, ax + o, ay + o, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, mode);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
@@ -539,7 +550,7 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         const size_t o = 32 * off;
         const int grid_h = grid_cap(ctx, bjjk::verify_hash_blocks_per_sm(), m);
         const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
-        int rc = ensure_table(ctx, ws, (size_t)grid_e * BJJ_BLOCK);
+        int rc = ensure_table(ctx, ws, 2 * (size_t)grid_e * BJJ_BLOCK);
         if (rc) return rc;
         ExactQueue q;     // never fed here (decompressed points are on the curve) but the kernel wants a valid one
         rc = ensure_queue(ctx, ws, 1, st, &q);
@@ -562,11 +573,16 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m, dax, day, status + off, 1);
         ctx->launches += 5;
         CU(ctx, cudaGetLastError());
-        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, status + off, hm, ok + off, false, q, q, ctx->flags_dev, BJJ_MODE_EDDSA,
-                          nullptr);
+        bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, sig64 + 2 * o, 2, 1, status + off, hm, ws->vs_lanes, ok + off, false, q,
+                          q, ctx->flags_dev, BJJ_MODE_EDDSA, ctx->verify_split, nullptr);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        bjjk::verify_ec(grid_e, st, m, dx, dy, sig64 + 2 * o, 2, 1, dax, day, hm, ok + off, ws->table, ctx->comb, BJJ_MODE_EDDSA);
+        if (ctx->verify_split) {
+            bjjk::verify_split(grid_cap(ctx, bjjk::verify_split_blocks_per_sm(), m), st, m, sig64 + 2 * o, 2, 1, hm, ws->vs_lanes, ok + off);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+        }
+        bjjk::verify_ec(grid_e, st, m, dx, dy, dax, day, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, BJJ_MODE_EDDSA);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
     }

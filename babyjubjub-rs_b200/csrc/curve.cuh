@@ -214,6 +214,50 @@ BJJ_HD void ext_add_niels_aff(PointExt& r, const PointExt& p, const NielsAff& n)
     if (WANT_T) fr_mul(r.T, e, h);
 }
 
+// Run-time flavours of the three formulas above, for loops that must keep ONE copy of each in the instruction
+// stream: a fully inlined field multiplication is ~3 KB of SASS, and a Straus window built from the templates
+// (4 doublings + 4 additions = 66 multiplications, 220 KB) runs out of instruction cache -- ncu showed 15
+// "no instruction" stall cycles per issue and a 21 % busy multiplier pipe (profiles/r1_ncu_icache_cliff.txt).
+BJJ_HD void ext_dbl_rt(PointExt& r, const PointExt& p, bool want_t) {
+    Fr xx, yy, zz2, s, e, g, f, h;
+    fr_sqr(xx, p.X);
+    fr_sqr(yy, p.Y);
+    fr_sqr(zz2, p.Z);
+    fr_dbl(zz2, zz2);
+    fr_add(s, p.X, p.Y);
+    fr_sqr(s, s);
+    fr_add(h, yy, xx);
+    fr_sub(g, yy, xx);
+    fr_sub(e, s, h);
+    fr_sub(f, zz2, g);
+    fr_mul(r.X, e, f);
+    fr_mul(r.Y, h, g);
+    fr_mul(r.Z, g, f);
+    if (want_t) fr_mul(r.T, e, h);
+}
+// r = p + n; `affine`: Z(n) = 1 (n.z2 is not read)
+BJJ_HD void ext_add_niels_rt(PointExt& r, const PointExt& p, const Niels& n, bool affine, bool want_t) {
+    Fr a, b, c, d, e, f, g, h, t;
+    fr_add(t, p.Y, p.X);
+    fr_mul(a, t, n.ypx);
+    fr_sub(t, p.Y, p.X);
+    fr_mul(b, t, n.ymx);
+    fr_mul(c, p.T, n.t2d);
+    if (affine) {
+        fr_dbl(d, p.Z);
+    } else {
+        fr_mul(d, p.Z, n.z2);
+    }
+    fr_sub(e, a, b);
+    fr_add(h, a, b);
+    fr_add(g, d, c);
+    fr_sub(f, d, c);
+    fr_mul(r.X, e, f);
+    fr_mul(r.Y, g, h);
+    fr_mul(r.Z, f, g);
+    if (want_t) fr_mul(r.T, e, h);
+}
+
 // a = -1 extended -> projective point on the ORIGINAL curve: (X / sqrt(-a) : Y : Z)
 BJJ_HD void ext_to_proj(PointProj& r, const PointExt& p) {
     const Fr si = fr_const(BJJ_INV_SQRT_NEG_A_M);

@@ -4,7 +4,7 @@
 // One verification is a short pipeline of kernels, so that no kernel carries another phase's registers
 // or instruction footprint:
 //   (bjj_cuda.cu: k_decompress_prepare / k_batch_inverse / k_decompress_finish for compressed input) ->
-//   k_verify_hash -> k_verify_ec || k_verify_exact
+//   k_verify_hash -> k_verify_split (EdDSA) -> k_verify_ec || k_verify_exact
 #include "kernels.h"
 
 using namespace bjj;
@@ -21,14 +21,20 @@ __global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_HASH_MINB) k_verify_hash
 #else
 __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
 #endif
-    size_t n, const uint8_t* r8x, const uint8_t* r8y,
-                                                           const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
-                                                           const uint8_t* skip, uint8_t* hm, uint8_t* ok, int gate,
-                                                           ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode,
-                                                           uint8_t* msg_status) {
+    size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
+    const uint8_t* s_base, size_t s_stride, size_t s_off, const uint8_t* skip, uint8_t* hm, size_t plane, uint8_t* ok,
+    int gate, ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode, int split, uint8_t* msg_status) {
     BJJ_FLAGS_BEGIN
-    BJJ_LANE_LOOP(n) lane_verify_hash(r8x, r8y, ax, ay, msg, skip, hm, ok, i, gate != 0, qa, qr, flags, mode, msg_status);
+    BJJ_LANE_LOOP(n)
+    lane_verify_hash(r8x, r8y, ax, ay, msg, s_base, s_stride, s_off, skip, hm, plane, ok, i, gate != 0, qa, qr, flags, mode,
+                     split != 0, msg_status);
     BJJ_FLAGS_END(gflags)
+}
+
+// half-size scalars (EdDSA lanes): pure integer-ALU work, small code, many resident warps
+__global__ void __launch_bounds__(BJJ_BLOCK, 4) k_verify_split(size_t n, const uint8_t* s_base, size_t s_stride, size_t s_off,
+                                                              uint8_t* hm, size_t plane, const uint8_t* ok) {
+    BJJ_LANE_LOOP(n) lane_verify_split(s_base, s_stride, s_off, hm, plane, ok, i);
 }
 
 // Register budget left to the compiler (239 registers, 2 CTAs per SM): capping it at 168 for a third CTA
@@ -36,11 +42,13 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
 // partitioned per SMSP (16,384 registers each), so the exact-lane kernel cannot co-reside with this one
 // whatever the cap; it runs on a side stream and fills the tail instead.
 __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
-                                                         const uint8_t* s_base, size_t s_stride, size_t s_off,
                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
-                                                         uint8_t* ok, U128* table, const CombEntry* comb, int mode) {
-    const LaneTable tbl = thread_table(table);
-    BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, i, tbl, comb, mode);
+                                                         size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
+                                                         int mode) {
+    // two per-thread radix-16 tables (multiples of 8A and of R8), back to back
+    const LaneTable tbl_a = thread_table(table);
+    const LaneTable tbl_r = thread_table(table + (size_t)BJJ_TABLE_U128_PER_LANE * gridDim.x * blockDim.x);
+    BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode);
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
@@ -69,16 +77,23 @@ static int occ(const void* k, int block) {
 }
 int verify_hash_blocks_per_sm() { return occ((const void*)k_verify_hash, BJJ_BLOCK); }
 int verify_ec_blocks_per_sm() { return occ((const void*)k_verify_ec, BJJ_BLOCK); }
+int verify_split_blocks_per_sm() { return occ((const void*)k_verify_split, BJJ_BLOCK); }
 
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
-                 const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
-                 ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode, uint8_t* msg_status) {
-    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, skip, hm, ok, gate ? 1 : 0, qa, qr, gflags, mode, msg_status);
+                 const uint8_t* ay, const uint8_t* msg, const uint8_t* s_base, size_t s_stride, size_t s_off,
+                 const uint8_t* skip, uint8_t* hm, size_t plane, uint8_t* ok, bool gate, ExactQueue qa, ExactQueue qr,
+                 uint32_t* gflags, int mode, bool split, uint8_t* msg_status) {
+    k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, s_base, s_stride, s_off, skip, hm, plane, ok, gate ? 1 : 0,
+                                              qa, qr, gflags, mode, split ? 1 : 0, msg_status);
 }
-void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
-               size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
-               U128* table, const CombEntry* comb, int mode) {
-    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, s_base, s_stride, s_off, ax, ay, hm, ok, table, comb, mode);
+void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, size_t s_stride, size_t s_off, uint8_t* hm,
+                  size_t plane, const uint8_t* ok) {
+    k_verify_split<<<grid, BJJ_BLOCK, 0, st>>>(n, s_base, s_stride, s_off, hm, plane, ok);
+}
+void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
+               const uint8_t* ay, const uint8_t* hm, size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
+               int mode) {
+    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode);
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb,

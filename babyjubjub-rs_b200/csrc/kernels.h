@@ -38,16 +38,20 @@ namespace bjjk {
 // resident CTAs per SM of the kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor), >= 1
 int verify_hash_blocks_per_sm();
 int verify_ec_blocks_per_sm();
+int verify_split_blocks_per_sm();
 int mul_scalar_blocks_per_sm();
 int sign_blocks_per_sm();
 int poseidon_blocks_per_sm(int t);
 
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
-                 const uint8_t* ay, const uint8_t* msg, const uint8_t* skip, uint8_t* hm, uint8_t* ok, bool gate,
-                 bjj::ExactQueue qa, bjj::ExactQueue qr, uint32_t* gflags, int mode, uint8_t* msg_status);
-void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base,
-               size_t s_stride, size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm, uint8_t* ok,
-               bjj::U128* table, const bjj::CombEntry* comb, int mode);
+                 const uint8_t* ay, const uint8_t* msg, const uint8_t* s_base, size_t s_stride, size_t s_off,
+                 const uint8_t* skip, uint8_t* hm, size_t plane, uint8_t* ok, bool gate, bjj::ExactQueue qa,
+                 bjj::ExactQueue qr, uint32_t* gflags, int mode, bool split, uint8_t* msg_status);
+void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, size_t s_stride, size_t s_off, uint8_t* hm,
+                  size_t plane, const uint8_t* ok);
+void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
+               const uint8_t* ay, const uint8_t* hm, size_t plane, uint8_t* ok, bjj::U128* table,
+               const bjj::CombEntry* comb, int mode);
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, bjj::ExactQueue qa, bjj::ExactQueue qr,
                   const bjj::CombEntry* comb, int mode);

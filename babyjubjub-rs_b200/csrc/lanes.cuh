@@ -11,6 +11,7 @@
 #include "curve.cuh"
 #include "fr.cuh"
 #include "poseidon.cuh"
+#include "split.cuh"
 
 namespace bjj {
 
@@ -104,6 +105,18 @@ BJJ_HD void table_load(Niels& n, const LaneTable& t, int e) {
     }
 }
 
+// L1 prefetch of the entry a later table_select(t, d) / comb_select(comb, w, d) will read (no registers held)
+#if BJJ_DEVICE_CODE
+#define BJJ_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#else
+#define BJJ_PREFETCH_L1(ptr) ((void)(ptr))
+#endif
+BJJ_HD void table_prefetch(const LaneTable& t, int d) {
+    const int e = d < 0 ? -d : d;
+#pragma unroll
+    for (int q = 0; q < 8; q++) BJJ_PREFETCH_L1(t.base + (size_t)(e * 8 + q) * t.stride + t.slot);
+}
+
 // entries 0..8 = j*P
 BJJ_HD void table_build(const LaneTable& t, const PointExt& p) {
     Niels n, n1;
@@ -111,12 +124,9 @@ BJJ_HD void table_build(const LaneTable& t, const PointExt& p) {
     table_store(t, 0, n);
     niels_from_ext(n1, p);
     table_store(t, 1, n1);
-    PointExt acc;
-    ext_dbl<true>(acc, p);
-    niels_from_ext(n, acc);
-    table_store(t, 2, n);
+    PointExt acc = p;      // 2P is P + P by the (complete) addition: same cost as a doubling, no second formula
 #pragma unroll 1
-    for (int j = 3; j <= 8; j++) {
+    for (int j = 2; j <= 8; j++) {
         ext_add_niels<true>(acc, acc, n1);
         niels_from_ext(n, acc);
         table_store(t, j, n);
@@ -147,6 +157,13 @@ void bjj_hostemu_need_entry(const struct CombEntry* comb, int w, int j);
 struct CombEntry {   // 96 bytes
     uint32_t ypx[8], ymx[8], t2d[8];
 };
+
+BJJ_HD void comb_prefetch(const CombEntry* comb, int w, int d) {
+    const int ad = d < 0 ? -d : d;
+    const uint8_t* e = reinterpret_cast<const uint8_t*>(comb + (size_t)w * BJJ_COMB_ENTRIES + ad);
+    BJJ_PREFETCH_L1(e);           // 96 bytes: at most two 128-byte lines
+    BJJ_PREFETCH_L1(e + 80);
+}
 
 BJJ_HD void comb_select(NielsAff& n, const CombEntry* comb, int w, int d) {
     int ad = d < 0 ? -d : d;
@@ -823,53 +840,103 @@ BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& m
     fr_from_mont(hm, st[0]);      // canonical integer hm < Q
 }
 
-// requires A and R8 ON the curve
-BJJ_HD uint32_t verify_fast(const PointAff& r8, const uint32_t* s, const PointAff& a, const Fr& hm,
-                            const LaneTable& tbl, const CombEntry* comb, int mode) {
-    PointExt pa, acc;
-    ext_from_affine(pa, a);
-    if (mode == BJJ_MODE_EDDSA) {       // (8*hm)*A = hm*(8A); Schnorr multiplies pk by h itself
-        ext_dbl<false>(pa, pa);
-        ext_dbl<false>(pa, pa);
-        ext_dbl<true>(pa, pa);
+// Scalars of one pending lane, written by the hash kernel (see split.cuh):
+//   u = v * hm (mod l) >= 0,  |v| odd with its sign in bit 255 of the stored word,  w = |v| * S (mod l).
+// verify_schnorr lanes (and BJJ_VERIFY_SPLIT=0) carry u = hm, v = 1, w = S.
+struct VerifyScalars {
+    uint32_t u[8], v[8], w[8];
+    uint32_t vneg;
+};
+
+// number of radix-16 windows a recoded scalar occupies (index of its highest non-zero digit + 1; 65 = carry)
+BJJ_HD int recode4_windows(const Recode4& rc) {
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t x = rc.w[k] ^ 0x88888888u;
+        if (x) n = 8 * k + ((35 - BJJ_CLZ32(x)) >> 2);
     }
-    // negate: (-X, Y, Z, -T)
-    fr_neg(pa.X, pa.X);
-    fr_neg(pa.T, pa.T);
-    table_build(tbl, pa);
-    Recode4 ra;
-    recode4(ra, hm.v);
-    Recode16 rs;
-    recode16(rs, s);
-    ext_identity(acc);
-    Niels nn;
-    NielsAff nb;
-    table_select(nn, tbl, (int)ra.top);
-    ext_add_niels<true>(acc, acc, nn);
-    comb_select(nb, comb, 0, (int)rs.top);
-    ext_add_niels_aff<false>(acc, acc, nb);
+    return rc.top ? 65 : n;
+}
+BJJ_HD int recode4_digit_any(const Recode4& rc, int i) {   // i in [0, 64]
+    return i == 64 ? (int)rc.top : recode4_digit(rc, i);
+}
+
+// requires A and R8 ON the curve.  Accepts iff  w*B8 - |v|*R8 - sign(v)*u*(8A) == O  (EdDSA; Schnorr: pk for 8A),
+// which for the scalars above is the reference's  S*B8 == R8 + (8*hm)*A.
+// One Straus pass over the two per-lane points (radix-16 tables in global memory) runs as many windows as
+// the wider of u, |v| needs (32-33 after the split, 64-65 without); w * B8 is 17 additions from the
+// fixed-base table afterwards.
+BJJ_HD uint32_t verify_fast(const PointAff& r8, const PointAff& a, const VerifyScalars& sc, const LaneTable& tbl_a,
+                            const LaneTable& tbl_r, const CombEntry* comb, int mode) {
+    PointExt acc;
+    // tables of -sign(v) * 8A (pk itself for Schnorr, which multiplies pk by h) and of -R8.  Every loop below is
+    // kept rolled: the kernel holds one inlined copy of the doubling and one of the addition (see curve.cuh).
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        ext_dbl<false>(acc, acc);
-        ext_dbl<false>(acc, acc);
-        ext_dbl<false>(acc, acc);
-        ext_dbl<true>(acc, acc);
-        table_select(nn, tbl, recode4_digit(ra, i));
-        if (i & 3) {
-            ext_add_niels<false>(acc, acc, nn);
-        } else {      // every fourth radix-16 window: one 16-bit digit of S against the B8 table
-            ext_add_niels<true>(acc, acc, nn);
-            comb_select(nb, comb, 0, recode16_digit(rs, i >> 2));
-            ext_add_niels_aff<false>(acc, acc, nb);
+    for (int t = 0; t < 2; t++) {
+        PointExt p;
+        ext_from_affine(p, t == 0 ? a : r8);
+        if (t == 0 && mode == BJJ_MODE_EDDSA) {
+#pragma unroll 1
+            for (int j = 0; j < 3; j++) ext_dbl_rt(p, p, j == 2);
         }
+        if (t == 1 || !sc.vneg) {       // negate: (-X, Y, Z, -T)
+            fr_neg(p.X, p.X);
+            fr_neg(p.T, p.T);
+        }
+        LaneTable tb = tbl_a;
+        if (t == 1) tb.base = tbl_r.base;
+        table_build(tb, p);
     }
-    // acc == R8 ?   X = x_R8 * sqrt(-a) * Z   and   Y = y_R8 * Z     (Z != 0: complete formulas)
-    const Fr sq = fr_const(BJJ_SQRT_NEG_A_M);
-    Fr lx, ly;
-    fr_mul(lx, r8.x, sq);
-    fr_mul(lx, lx, acc.Z);
-    fr_mul(ly, r8.y, acc.Z);
-    return (fr_eq(lx, acc.X) && fr_eq(ly, acc.Y)) ? 1u : 0u;
+    Recode4 ru, rv;
+    recode4(ru, sc.u);
+    recode4(rv, sc.v);
+    Recode16 rw;
+    recode16(rw, sc.w);
+    int nwin = recode4_windows(ru);
+    const int nv = recode4_windows(rv);
+    nwin = nwin > nv ? nwin : nv;
+    // Uniform trip counts matter beyond divergence: the warps of an SM share the instruction cache only while
+    // they run the same stretch of this (large) loop body, and a warp that finishes a lane one window early is
+    // out of step for good.  33 windows cover all but ~0.2 % of the split scalars.
+    nwin = nwin < 33 ? 33 : nwin;
+#if BJJ_DEVICE_CODE
+    // one trip count per warp: the lanes stay converged and reach the B8 windows together (the extra leading
+    // digits of a narrower lane are zero = the identity entry)
+    nwin = __reduce_max_sync(__activemask(), nwin);
+#endif
+    ext_identity(acc);
+    // Straus pass over the two per-lane tables: four doublings and two additions per window, as ONE straight-line
+    // body.  Its size matters: at ~160 KB of SASS the instruction prefetcher keeps the multiplier pipe 85 % busy,
+    // at 200 KB the same code ran 4x slower (profiles/r1_ncu_icache_cliff.txt), and a body rolled into
+    // per-formula loops pays a fetch bubble per backward branch -- so the B8 additions live in their own loop.
+#pragma unroll 1
+    for (int i = nwin - 1; i >= 0; i--) {
+        if (i != nwin - 1) {
+            ext_dbl<false>(acc, acc);
+            ext_dbl<false>(acc, acc);
+            ext_dbl<false>(acc, acc);
+            ext_dbl<true>(acc, acc);
+        }
+        Niels nn;
+        table_select(nn, tbl_a, recode4_digit_any(ru, i));
+        ext_add_niels<true>(acc, acc, nn);
+        table_select(nn, tbl_r, recode4_digit_any(rv, i));
+        ext_add_niels_rt(acc, acc, nn, false, i == 0);      // T only where the B8 additions follow
+    }
+    // + w * B8: 16 signed 16-bit digits and the recoding carry against the fixed-base table, no doubling
+#pragma unroll 1
+    for (int k = BJJ_COMB_WINDOWS - 1; k >= 0; k--) {
+        NielsAff nb;
+        comb_select(nb, comb, k, k == BJJ_COMB_WINDOWS - 1 ? (int)rw.top : recode16_digit(rw, k));
+        Niels nn;
+        nn.ypx = nb.ypx;
+        nn.ymx = nb.ymx;
+        nn.t2d = nb.t2d;
+        ext_add_niels_rt(acc, acc, nn, true, k != 0);
+    }
+    // acc == O = (0 : 1 : 1) ?   (Z != 0: complete formulas)
+    return (fr_is_zero(acc.X) && fr_eq(acc.Y, acc.Z)) ? 1u : 0u;
 }
 
 // Exact lanes of verify: taken when R8 or A is not on the curve (the hash kernel has already stored hm).
@@ -951,10 +1018,13 @@ BJJ_HD uint32_t verify_exact(const PointAff& r8, const uint32_t* s, const PointA
 //   phase 3 (lane_verify_exact, other kernel): the queued off-curve lanes.
 // `skip` (may be null): lanes whose decompression failed (verify_compressed) are rejected up front.
 #define BJJ_OK_PENDING 2
+// hm_out: 4 planes of `plane` 32-byte elements: hm | u | v (sign in bit 255) | w.
+// S of lane i sits at 32-byte element index i * s_stride + s_off (1, 0 for a plain S array; 2, 1 inside sig64).
 BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
-                             const uint8_t* msg32, const uint8_t* skip, uint8_t* hm_out, uint8_t* ok, size_t i,
+                             const uint8_t* msg32, const uint8_t* s_base, size_t s_stride, size_t s_off,
+                             const uint8_t* skip, uint8_t* hm_out, size_t plane, uint8_t* ok, size_t i,
                              bool gate, const ExactQueue& qa, const ExactQueue& qr, uint32_t& flags, int mode,
-                             uint8_t* msg_status) {
+                             bool split, uint8_t* msg_status) {
     if (skip && skip[i]) {
         ok[i] = 0;
         return;
@@ -991,23 +1061,50 @@ BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8
     verify_hm(hm, r8, a, mm, mode);
     store_u256(hm_out, i, hm.v);
     ok[i] = (uint8_t)state;
+    // scalars of the Straus pass: full width here (u = hm, v = 1, w = S); lane_verify_split shortens them
+    if (state != BJJ_OK_PENDING || (split && mode == BJJ_MODE_EDDSA)) return;
+    uint32_t sv[8], one[8];
+    load_u256(sv, s_base, i * s_stride + s_off);
+#pragma unroll
+    for (int k = 0; k < 8; k++) one[k] = k == 0 ? 1u : 0u;
+    store_u256(hm_out, plane + i, hm.v);
+    store_u256(hm_out, 2 * plane + i, one);
+    store_u256(hm_out, 3 * plane + i, sv);
 }
 
-// S of lane i sits at 32-byte element index i * s_stride + s_off (1, 0 for a plain S array; 2, 1 inside sig64)
-BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s_base, size_t s_stride,
-                           size_t s_off, const uint8_t* ax, const uint8_t* ay, const uint8_t* hm_in, uint8_t* ok,
-                           size_t i, const LaneTable& tbl, const CombEntry* comb, int mode) {
+// phase 1b (EdDSA): half-size scalars for the pending lanes (split.cuh).  Its own kernel: integer-ALU work with
+// lane-dependent trip counts, which inside the hash kernel would leave that kernel's warps out of step.
+BJJ_HD void lane_verify_split(const uint8_t* s_base, size_t s_stride, size_t s_off, uint8_t* hm_io, size_t plane,
+                              const uint8_t* ok, size_t i) {
     if (ok[i] != BJJ_OK_PENDING) return;
-    uint32_t s[8], flags = 0;
+    uint32_t hm[8], sv[8], u[8], v[8], w[8], vneg = 0;
+    load_u256(hm, hm_io, i);
+    load_u256(sv, s_base, i * s_stride + s_off);
+    split_scalars(u, v, vneg, hm);
+    split_scale_s(w, sv, v);
+    v[7] |= vneg << 31;
+    store_u256(hm_io, plane + i, u);
+    store_u256(hm_io, 2 * plane + i, v);
+    store_u256(hm_io, 3 * plane + i, w);
+}
+
+BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
+                           const uint8_t* hm_in, size_t plane, uint8_t* ok, size_t i, const LaneTable& tbl_a,
+                           const LaneTable& tbl_r, const CombEntry* comb, int mode) {
+    if (ok[i] != BJJ_OK_PENDING) return;
+    uint32_t flags = 0;
     PointAff r8, a;
-    Fr hm;
-    load_u256(s, s_base, i * s_stride + s_off);
-    load_u256(hm.v, hm_in, i);
+    VerifyScalars sc;
+    load_u256(sc.u, hm_in, plane + i);
+    load_u256(sc.v, hm_in, 2 * plane + i);
+    load_u256(sc.w, hm_in, 3 * plane + i);
+    sc.vneg = sc.v[7] >> 31;
+    sc.v[7] &= 0x7FFFFFFFu;
     load_fr(r8.x, r8x, i, flags);
     load_fr(r8.y, r8y, i, flags);
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
-    ok[i] = (uint8_t)verify_fast(r8, s, a, hm, tbl, comb, mode);
+    ok[i] = (uint8_t)verify_fast(r8, a, sc, tbl_a, tbl_r, comb, mode);
 }
 
 template <bool A_OFF>

@@ -226,6 +226,9 @@ def emit(out):
     ]
     for name, val in singles:
         w("BJJ_CONST uint32_t BJJ_%s[8] = %s;\n" % (name, fmt(val)))
+    # Montgomery arithmetic modulo l = SUBORDER (verify's half-size scalar split)
+    w("#define BJJ_L_NINV32 0x%08xu   // -l^-1 mod 2^32\n" % ((-pow(SUBORDER, -1, 1 << 32)) % (1 << 32)))
+    w("BJJ_CONST uint32_t BJJ_L_R2[8] = %s;   // 2^512 mod l\n" % fmt(pow(2, 512, SUBORDER)))
     w("\n")
 
     # exponent bits for Fermat inversion (Q-2) and sqrt ((T-1)/2 with Q-1 = 2^28*T)

@@ -14,6 +14,7 @@ using namespace bjj;
 
 static CombEntry* g_comb = nullptr;
 static uint8_t* g_comb_valid = nullptr;
+static bool g_split = true;
 
 // comb entries are built on demand (the device builds all 524,290 in k_comb_build; here a test touches a few)
 namespace bjj {
@@ -24,7 +25,7 @@ void bjj_hostemu_need_entry(const CombEntry* comb, int w, int j) {
     comb_build_entry(g_comb, w, j);
 }
 }  // namespace bjj
-static std::vector<U128> g_table(BJJ_TABLE_U128_PER_LANE);
+static std::vector<U128> g_table(2 * BJJ_TABLE_U128_PER_LANE);
 
 static std::vector<uint32_t> g_list, g_list2;
 static uint32_t g_count, g_count2;
@@ -61,9 +62,9 @@ static void batch_affine(const ProjScratch& s, uint8_t* rx, uint8_t* ry, size_t 
     for (size_t t = 0; t < T; t++) batch_affine_strided(s, rx, ry, n, t, T);
 }
 
-static LaneTable lane_table() {
+static LaneTable lane_table(int which = 0) {
     LaneTable t;
-    t.base = g_table.data();
+    t.base = g_table.data() + (size_t)which * BJJ_TABLE_U128_PER_LANE;
     t.stride = 1;
     t.slot = 0;
     return t;
@@ -187,9 +188,12 @@ uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint
     emu_init();
     uint32_t flags = 0;
     ExactQueue qa = exact_queue(n), qr = exact_queue2(n);
-    std::vector<uint8_t> hm(32 * (n + 1));
-    for (size_t i = 0; i < n; i++) lane_verify_hash(r8x, r8y, ax, ay, msg, nullptr, hm.data(), ok, i, true, qa, qr, flags, BJJ_MODE_EDDSA, nullptr);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, s, 1, 0, ax, ay, hm.data(), ok, i, lane_table(), g_comb, BJJ_MODE_EDDSA);
+    std::vector<uint8_t> hm(4 * 32 * (n + 1));
+    for (size_t i = 0; i < n; i++)
+        lane_verify_hash(r8x, r8y, ax, ay, msg, s, 1, 0, nullptr, hm.data(), n, ok, i, true, qa, qr, flags, BJJ_MODE_EDDSA, g_split, nullptr);
+    if (g_split)
+        for (size_t i = 0; i < n; i++) lane_verify_split(s, 1, 0, hm.data(), n, ok, i);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, ax, ay, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_EDDSA);
     for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list[j], g_comb, BJJ_MODE_EDDSA);
     for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list2[j], g_comb, BJJ_MODE_EDDSA);
     return flags;
@@ -200,10 +204,10 @@ uint32_t emu_verify_schnorr(size_t n, const uint8_t* pkx, const uint8_t* pky, co
     emu_init();
     uint32_t flags = 0;
     ExactQueue qa = exact_queue(n), qr = exact_queue2(n);
-    std::vector<uint8_t> hm(32 * (n + 1));
+    std::vector<uint8_t> hm(4 * 32 * (n + 1));
     for (size_t i = 0; i < n; i++)
-        lane_verify_hash(rx, ry, pkx, pky, msg, nullptr, hm.data(), ok, i, true, qa, qr, flags, BJJ_MODE_SCHNORR, status);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(rx, ry, s, 1, 0, pkx, pky, hm.data(), ok, i, lane_table(), g_comb, BJJ_MODE_SCHNORR);
+        lane_verify_hash(rx, ry, pkx, pky, msg, s, 1, 0, nullptr, hm.data(), n, ok, i, true, qa, qr, flags, BJJ_MODE_SCHNORR, g_split, status);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(rx, ry, pkx, pky, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_SCHNORR);
     for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(rx, ry, s, pkx, pky, hm.data(), ok, g_list[j], g_comb, BJJ_MODE_SCHNORR);
     for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(rx, ry, s, pkx, pky, hm.data(), ok, g_list2[j], g_comb, BJJ_MODE_SCHNORR);
     return flags;
@@ -212,7 +216,7 @@ uint32_t emu_verify_schnorr(size_t n, const uint8_t* pkx, const uint8_t* pky, co
 void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msg, uint8_t* ok,
                            uint8_t* status) {
     emu_init();
-    std::vector<uint8_t> d(4 * 32 * (n + 1)), hm(32 * (n + 1));
+    std::vector<uint8_t> d(4 * 32 * (n + 1)), hm(4 * 32 * (n + 1));
     uint8_t *dx = d.data(), *dy = dx + 32 * n, *ax = dy + 32 * n, *ay = ax + 32 * n;
     uint32_t flags = 0;
     ExactQueue q = exact_queue(n);
@@ -222,8 +226,27 @@ void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, 
     batch_inverse(scr, 2 * n);
     for (size_t i = 0; i < n; i++) lane_decompress_finish(sig64, 2, 0, scr, i, dx, dy, status, i, false);
     for (size_t i = 0; i < n; i++) lane_decompress_finish(pk32, 1, 0, scr, n + i, ax, ay, status, i, true);
-    for (size_t i = 0; i < n; i++) lane_verify_hash(dx, dy, ax, ay, msg, status, hm.data(), ok, i, false, q, q, flags, BJJ_MODE_EDDSA, nullptr);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, sig64, 2, 1, ax, ay, hm.data(), ok, i, lane_table(), g_comb, BJJ_MODE_EDDSA);
+    for (size_t i = 0; i < n; i++)
+        lane_verify_hash(dx, dy, ax, ay, msg, sig64, 2, 1, status, hm.data(), n, ok, i, false, q, q, flags, BJJ_MODE_EDDSA, g_split, nullptr);
+    if (g_split)
+        for (size_t i = 0; i < n; i++) lane_verify_split(sig64, 2, 1, hm.data(), n, ok, i);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, ax, ay, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_EDDSA);
+}
+
+// verify's half-size scalar split (split.cuh), for the invariant tests: u = v * h (mod l), v odd
+void emu_set_split(int on) { g_split = on != 0; }
+void emu_split(size_t n, const uint8_t* h32, const uint8_t* s32, uint8_t* u32, uint8_t* v32, uint8_t* vneg, uint8_t* w32) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t h[8], s[8], u[8], v[8], w[8], neg = 0;
+        load_u256(h, h32, i);
+        load_u256(s, s32, i);
+        split_scalars(u, v, neg, h);
+        split_scale_s(w, s, v);
+        store_u256(u32, i, u);
+        store_u256(v32, i, v);
+        store_u256(w32, i, w);
+        vneg[i] = (uint8_t)neg;
+    }
 }
 
 }  // extern "C"
