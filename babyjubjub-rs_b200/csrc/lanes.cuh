@@ -152,7 +152,7 @@ BJJ_HD void table_select(Niels& n, const LaneTable& t, int d) {
 #define BJJ_COMB_TOTAL ((size_t)(BJJ_COMB_WINDOWS - 1) * BJJ_COMB_ENTRIES + 2)
 #if !BJJ_DEVICE_CODE && defined(BJJ_HOST_EMU)
 // the host test harness fills table entries on demand instead of building all 524,290 of them
-void bjj_hostemu_need_entry(const struct CombEntry* comb, int w, int j);
+void bjj_emu_need_comb_entry(const struct CombEntry* comb, int w, int j);
 #endif
 struct CombEntry {   // 96 bytes
     uint32_t ypx[8], ymx[8], t2d[8];
@@ -169,7 +169,7 @@ BJJ_HD void comb_select(NielsAff& n, const CombEntry* comb, int w, int d) {
     int ad = d < 0 ? -d : d;
     const CombEntry* e = comb + (size_t)w * BJJ_COMB_ENTRIES + ad;
 #if !BJJ_DEVICE_CODE && defined(BJJ_HOST_EMU)
-    bjj_hostemu_need_entry(comb, w, ad);
+    bjj_emu_need_comb_entry(comb, w, ad);
 #endif
 #if BJJ_DEVICE_CODE
     const uint4* p = reinterpret_cast<const uint4*>(e);

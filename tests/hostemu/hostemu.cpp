@@ -18,7 +18,7 @@ static bool g_split = true;
 
 // comb entries are built on demand (the device builds all 524,290 in k_comb_build; here a test touches a few)
 namespace bjj {
-void bjj_hostemu_need_entry(const CombEntry* comb, int w, int j) {
+void bjj_emu_need_comb_entry(const CombEntry* comb, int w, int j) {
     const size_t idx = (size_t)w * BJJ_COMB_ENTRIES + j;
     if (comb != g_comb || g_comb_valid[idx]) return;
     g_comb_valid[idx] = 1;
