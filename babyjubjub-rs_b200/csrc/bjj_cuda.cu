@@ -16,6 +16,7 @@ using namespace bjj;
 
 #define BJJ_PIPE_SLOTS 2
 #define BJJ_CHUNK_LANES (1u << 20)
+#define BJJ_CHUNK_RAMP_LANES ((size_t)1 << 18)   // first chunk of a long host call (see run_host)
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
@@ -109,11 +110,18 @@ struct Workspace {
     cudaEvent_t ev_fork, ev_join;
 };
 
+// one of the two staging buffers of the host-pointer flavour: a copy stream, a device arena, and the events that
+// order its copies against the (single) compute stream
 struct PipeSlot {
     cudaStream_t stream;
     uint8_t* arena;
     size_t arena_bytes;
-    Workspace ws;
+    cudaEvent_t ev_in, ev_out;
+};
+// what a launch runs on
+struct ComputeRef {
+    cudaStream_t stream;
+    Workspace& ws;
 };
 
 struct bjj_ctx {
@@ -121,7 +129,8 @@ struct bjj_ctx {
     int sms;
     cudaStream_t stream;        // stream of the _dev flavour when the caller passes NULL
     CombEntry* comb;
-    Workspace ws;               // workspace of the _dev flavour (host calls use their pipeline slot's)
+    Workspace ws;               // scratch of the kernels; all compute of a context runs on one stream at a time
+    Workspace ws2;              // second set: the host flavour alternates, so a chunk's exact lanes may outlive it
     uint32_t* flags_dev;
     uint32_t* flags_host;       // pinned
     PipeSlot slot[BJJ_PIPE_SLOTS];
@@ -310,10 +319,12 @@ void bjj_destroy(bjj_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int s = 0; s < BJJ_PIPE_SLOTS; s++) {
         if (ctx->slot[s].arena) cudaFree(ctx->slot[s].arena);
-        free_workspace(&ctx->slot[s].ws);
+        if (ctx->slot[s].ev_in) cudaEventDestroy(ctx->slot[s].ev_in);
+        if (ctx->slot[s].ev_out) cudaEventDestroy(ctx->slot[s].ev_out);
         if (ctx->slot[s].stream) cudaStreamDestroy(ctx->slot[s].stream);
     }
     free_workspace(&ctx->ws);
+    free_workspace(&ctx->ws2);
     if (ctx->comb) cudaFree(ctx->comb);
     if (ctx->flags_dev) cudaFree(ctx->flags_dev);
     if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
@@ -348,7 +359,11 @@ int bjj_init(int device, bjj_ctx** out) {
     INIT_CU(cudaGetDeviceProperties(&prop, device));
     ctx->sms = prop.multiProcessorCount;
     INIT_CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (int s = 0; s < BJJ_PIPE_SLOTS; s++) INIT_CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
+    for (int s = 0; s < BJJ_PIPE_SLOTS; s++) {
+        INIT_CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
+        INIT_CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_in, cudaEventDisableTiming));
+        INIT_CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_out, cudaEventDisableTiming));
+    }
     INIT_CU(cudaMalloc(&ctx->flags_dev, sizeof(uint32_t)));
     INIT_CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(uint32_t), ctx->stream));
     INIT_CU(cudaHostAlloc(&ctx->flags_host, sizeof(uint32_t), cudaHostAllocDefault));
@@ -482,7 +497,7 @@ static int ensure_vscratch(bjj_ctx* ctx, Workspace* ws, size_t lanes, uint8_t** 
 // mode: BJJ_MODE_EDDSA (verify) or BJJ_MODE_SCHNORR (verify_schnorr; msg_status receives the per-lane Err)
 static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                          const uint8_t* ax, const uint8_t* ay, const uint8_t* msg, uint8_t* ok, cudaStream_t st,
-                         Workspace* ws, int mode = BJJ_MODE_EDDSA, uint8_t* msg_status = nullptr) {
+                         Workspace* ws, int mode = BJJ_MODE_EDDSA, uint8_t* msg_status = nullptr, bool defer_join = false) {
     for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
         const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
         const size_t o = 32 * off;
@@ -498,6 +513,8 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         if (rc) return rc;
         rc = ensure_aux(ctx, ws);
         if (rc) return rc;
+        // exact lanes of an earlier batch may still be reading this workspace's scratch (deferred join)
+        CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
         // BJJ_PHASE_TIMING=1: synchronous per-phase CUDA-event timings on stderr (diagnosis only)
         static const bool phase_timing = getenv("BJJ_PHASE_TIMING") != nullptr;
         cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -528,7 +545,9 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
         if (phase_timing) cudaEventRecord(pe[2], st);
-        CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
+        // defer_join: the caller orders whatever consumes ok[] after ws->ev_join itself, and the stream moves on
+        // to the next batch while the (latency-bound) exact lanes finish beside it
+        if (!defer_join) CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
         if (phase_timing) {
             cudaEventRecord(pe[3], st);
             cudaEventSynchronize(pe[3]);
@@ -713,6 +732,12 @@ struct HostArg {
     size_t bytes_per_lane;
 };
 
+// Copies and kernels overlap, kernels never overlap each other: every kernel of this library is sized to fill
+// the GPU and streams a large instruction footprint, and two of them sharing SMs starve each other's
+// instruction fetch (measured: two concurrent verify pipelines ran at 0.65x the serial rate).  So the two slots
+// only own copy streams and staging arenas; all launches go to the context's one compute stream, ordered against
+// the copies by events.  Chunk sizes ramp up (2^18, 2^19, BJJ_CHUNK_LANES) so that only the first, small
+// host-to-device copy is exposed.
 template <class Launch>
 static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch launch) {
     if (!ctx) return BJJ_ERR_ARG;
@@ -720,27 +745,26 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         if (!args[a].in && !args[a].out) return BJJ_ERR_ARG;
     if (n == 0) return BJJ_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    size_t lane_bytes = 0;
-    for (int a = 0; a < nargs; a++) lane_bytes += (args[a].bytes_per_lane + 15) & ~(size_t)15;
     const size_t chunk = n < BJJ_CHUNK_LANES ? n : BJJ_CHUNK_LANES;
     // every array slice starts 256-byte aligned inside the arena
     size_t need = 0;
     for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * chunk + 255) & ~(size_t)255);
-    (void)lane_bytes;
     int rc = BJJ_OK;
     int which = 0;
-    for (size_t off = 0; off < n; off += chunk, which ^= 1) {
+    size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
+    size_t m = 0;
+    for (size_t off = 0; off < n; off += m, which ^= 1, cur = (2 * cur < chunk ? 2 * cur : chunk)) {
         PipeSlot& sl = ctx->slot[which];
-        const size_t m = (n - off) < chunk ? (n - off) : chunk;
-        // the slot's previous chunk must have drained before its arena is reused
-        CU(ctx, cudaStreamSynchronize(sl.stream));
+        m = (n - off) < cur ? (n - off) : cur;
         if (sl.arena_bytes < need) {
+            CU(ctx, cudaStreamSynchronize(sl.stream));
             if (sl.arena) cudaFree(sl.arena);
             sl.arena = nullptr;
             sl.arena_bytes = 0;
             CU(ctx, cudaMalloc(&sl.arena, need));
             sl.arena_bytes = need;
         }
+        // the slot's copy stream is ordered: these copies follow the slot's previous results going out
         uint8_t* dptr[16];
         size_t pos = 0;
         for (int a = 0; a < nargs; a++) {
@@ -750,8 +774,14 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
                 CU(ctx, cudaMemcpyAsync(dptr[a], args[a].in + off * args[a].bytes_per_lane, m * args[a].bytes_per_lane,
                                         cudaMemcpyHostToDevice, sl.stream));
         }
-        rc = launch(m, dptr, sl);
+        ComputeRef comp{ctx->stream, which ? ctx->ws2 : ctx->ws};
+        CU(ctx, cudaEventRecord(sl.ev_in, sl.stream));
+        CU(ctx, cudaStreamWaitEvent(comp.stream, sl.ev_in, 0));
+        rc = launch(m, dptr, comp);
         if (rc) return rc;
+        CU(ctx, cudaEventRecord(sl.ev_out, comp.stream));
+        CU(ctx, cudaStreamWaitEvent(sl.stream, sl.ev_out, 0));
+        if (comp.ws.aux) CU(ctx, cudaStreamWaitEvent(sl.stream, comp.ws.ev_join, 0));      // deferred exact lanes
         for (int a = 0; a < nargs; a++)
             if (args[a].out)
                 CU(ctx, cudaMemcpyAsync(args[a].out + off * args[a].bytes_per_lane, dptr[a], m * args[a].bytes_per_lane,
@@ -773,7 +803,7 @@ int bjj_fr_op_batch(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint
     if (!ctx || !a || !out || op < 0 || op > 4) return BJJ_ERR_ARG;
     if (!b) b = a;
     HostArg args[] = {H_IN(a, 32), H_IN(b, 32), H_OUT(out, 32)};
-    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         k_fr_op<<<grid_for(ctx, (const void*)k_fr_op, m), BJJ_BLOCK, 0, sl.stream>>>(op, m, d[0], d[1], d[2], ctx->flags_dev);
         CHECK_LAUNCH(ctx)
     });
@@ -784,7 +814,7 @@ int bjj_add_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, 
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(pz, 32), H_IN(qx, 32), H_IN(qy, 32),
                       H_IN(qz, 32), H_OUT(rx, 32), H_OUT(ry, 32), H_OUT(rz, 32)};
-    return run_host(ctx, n, args, 9, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 9, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         k_add<<<grid_for(ctx, (const void*)k_add, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4], d[5], d[6],
                                                                                 d[7], d[8], ctx->flags_dev);
         CHECK_LAUNCH(ctx)
@@ -795,7 +825,7 @@ int bjj_affine_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* p
                      uint8_t* ry) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(pz, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
-    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         k_affine<<<grid_for(ctx, (const void*)k_affine, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4],
                                                                                       ctx->flags_dev);
         CHECK_LAUNCH(ctx)
@@ -806,7 +836,7 @@ int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_
                          uint8_t* rx, uint8_t* ry) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
-    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_mul_scalar(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.ws);
     });
 }
@@ -814,7 +844,7 @@ int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_
 int bjj_fixed_base_batch(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
-    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_fixed_base(ctx, m, d[0], d[1], d[2], false, sl.stream, &sl.ws);
     });
 }
@@ -822,7 +852,7 @@ int bjj_fixed_base_batch(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_
 int bjj_public_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* rx, uint8_t* ry) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(key32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
-    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_fixed_base(ctx, m, d[0], d[1], d[2], true, sl.stream, &sl.ws);
     });
 }
@@ -831,7 +861,7 @@ int bjj_sign_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* 
                    uint8_t* s32, uint8_t* status) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(key32, 32), H_IN(msg32, 32), H_OUT(r8x, 32), H_OUT(r8y, 32), H_OUT(s32, 32), H_OUT(status, 1)};
-    return run_host(ctx, n, args, 6, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 6, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         bjjk::sign(grid_cap(ctx, bjjk::sign_blocks_per_sm(), m), sl.stream, m, d[0], d[1], d[2], d[3], d[4], d[5], ctx->comb);
         CHECK_LAUNCH(ctx)
     });
@@ -840,7 +870,7 @@ int bjj_sign_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* 
 int bjj_scalar_key_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* scalar32) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(key32, 32), H_OUT(scalar32, 32)};
-    return run_host(ctx, n, args, 2, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 2, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         k_scalar_key<<<grid_for(ctx, (const void*)k_scalar_key, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1]);
         CHECK_LAUNCH(ctx)
     });
@@ -849,7 +879,7 @@ int bjj_scalar_key_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* 
 int bjj_compress_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, uint8_t* out32) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_OUT(out32, 32)};
-    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         k_compress<<<grid_for(ctx, (const void*)k_compress, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], ctx->flags_dev);
         CHECK_LAUNCH(ctx)
     });
@@ -858,7 +888,7 @@ int bjj_compress_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t*
 int bjj_decompress_batch(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* rx, uint8_t* ry, uint8_t* status) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(in32, 32), H_OUT(rx, 32), H_OUT(ry, 32), H_OUT(status, 1)};
-    return run_host(ctx, n, args, 4, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 4, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_decompress(ctx, m, d[0], d[1], d[2], d[3], sl.stream, &sl.ws);
     });
 }
@@ -868,7 +898,7 @@ int bjj_poseidon_batch(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* cons
     HostArg args[9];
     for (int j = 0; j < n_inputs; j++) args[j] = H_IN(in[j], 32);
     args[n_inputs] = H_OUT(out, 32);
-    return run_host(ctx, n, args, n_inputs + 1, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, n_inputs + 1, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_poseidon(ctx, n_inputs, m, (const uint8_t* const*)d, d[n_inputs], sl.stream);
     });
 }
@@ -877,8 +907,8 @@ int bjj_verify_batch(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* 
                      const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(r8x, 32), H_IN(r8y, 32), H_IN(s32, 32), H_IN(ax, 32), H_IN(ay, 32), H_IN(msg32, 32), H_OUT(ok, 1)};
-    return run_host(ctx, n, args, 7, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.ws);
+    return run_host(ctx, n, args, 7, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
+        return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.ws, BJJ_MODE_EDDSA, nullptr, true);
     });
 }
 
@@ -887,8 +917,8 @@ int bjj_verify_schnorr_batch(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const u
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(pkx, 32), H_IN(pky, 32), H_IN(msg32, 32), H_IN(rx, 32), H_IN(ry, 32), H_IN(s32, 32), H_OUT(ok, 1),
                       H_OUT(status, 1)};
-    return run_host(ctx, n, args, 8, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
-        return launch_verify(ctx, m, d[3], d[4], d[5], d[0], d[1], d[2], d[6], sl.stream, &sl.ws, BJJ_MODE_SCHNORR, d[7]);
+    return run_host(ctx, n, args, 8, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
+        return launch_verify(ctx, m, d[3], d[4], d[5], d[0], d[1], d[2], d[6], sl.stream, &sl.ws, BJJ_MODE_SCHNORR, d[7], true);
     });
 }
 
@@ -896,7 +926,7 @@ int bjj_verify_compressed_batch(bjj_ctx* ctx, size_t n, const uint8_t* sig64, co
                                 const uint8_t* msg32, uint8_t* ok, uint8_t* status) {
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(sig64, 64), H_IN(pk32, 32), H_IN(msg32, 32), H_OUT(ok, 1), H_OUT(status, 1)};
-    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, PipeSlot& sl) -> int {
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_verify_compressed(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.ws);
     });
 }
