@@ -214,10 +214,9 @@ BJJ_HD void ext_add_niels_aff(PointExt& r, const PointExt& p, const NielsAff& n)
     if (WANT_T) fr_mul(r.T, e, h);
 }
 
-// Run-time flavours of the three formulas above, for loops that must keep ONE copy of each in the instruction
-// stream: a fully inlined field multiplication is ~3 KB of SASS, and a Straus window built from the templates
-// (4 doublings + 4 additions = 66 multiplications, 220 KB) runs out of instruction cache -- ncu showed 15
-// "no instruction" stall cycles per issue and a 21 % busy multiplier pipe (profiles/r1_ncu_icache_cliff.txt).
+// Run-time flavours of the formulas above, for the short loops around the Straus pass (table set-up, B8
+// additions) that keep ONE copy of a formula in the instruction stream: a fully inlined field multiplication is
+// ~3 KB of SASS.  The hot window body itself stays straight-line (see verify_fast).
 BJJ_HD void ext_dbl_rt(PointExt& r, const PointExt& p, bool want_t) {
     Fr xx, yy, zz2, s, e, g, f, h;
     fr_sqr(xx, p.X);

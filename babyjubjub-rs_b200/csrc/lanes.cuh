@@ -897,8 +897,9 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const PointAff& a, const VerifyS
     const int nv = recode4_windows(rv);
     nwin = nwin > nv ? nwin : nv;
     // Uniform trip counts matter beyond divergence: the warps of an SM share the instruction cache only while
-    // they run the same stretch of this (large) loop body, and a warp that finishes a lane one window early is
-    // out of step for good.  33 windows cover all but ~0.2 % of the split scalars.
+    // they run the same stretch of the (large) loop body below, and a warp that finishes a lane one window early
+    // is out of step for good -- with per-warp counts of 32-34 this kernel ran 2x slower (no_instruction stalls
+    // 2.0 per issue against 0.85).  33 windows cover all but ~0.2 % of the split scalars.
     nwin = nwin < 33 ? 33 : nwin;
 #if BJJ_DEVICE_CODE
     // one trip count per warp: the lanes stay converged and reach the B8 windows together (the extra leading
@@ -906,10 +907,11 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const PointAff& a, const VerifyS
     nwin = __reduce_max_sync(__activemask(), nwin);
 #endif
     ext_identity(acc);
-    // Straus pass over the two per-lane tables: four doublings and two additions per window, as ONE straight-line
-    // body.  Its size matters: at ~160 KB of SASS the instruction prefetcher keeps the multiplier pipe 85 % busy,
-    // at 200 KB the same code ran 4x slower (profiles/r1_ncu_icache_cliff.txt), and a body rolled into
-    // per-formula loops pays a fetch bubble per backward branch -- so the B8 additions live in their own loop.
+    // Straus pass over the two per-lane tables: four doublings and two additions per window as ONE straight-line
+    // body (~150 KB of SASS) that the instruction prefetcher can follow; rolled into per-formula loops the same
+    // work ran 1.4x slower (a fetch bubble per backward branch).  The B8 additions live in their own short loop.
+    // What this kernel is most sensitive to is instruction supply: see the note on nwin above and
+    // profiles/r1_ncu_icache_cliff.txt.
 #pragma unroll 1
     for (int i = nwin - 1; i >= 0; i--) {
         if (i != nwin - 1) {

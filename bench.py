@@ -41,16 +41,21 @@ UNIT = "verifies/s"
 # product of N terms = 64 N + 64.  Counts are for the algorithms actually built; derivations in DESIGN.md section 6.
 FMUL = 128
 ALGO_FMUL = {
-    # gates 10 + Montgomery conversions 10 + map 2 + 8A 22 + table 64 + first adds 15
-    # + 16 x (4 x (3 x 7 + 8) + 3 x 7 + 8 + 6) Straus windows (one 16-bit B8 digit per 4 nibbles of hm) + compare 3
-    "verify_ec": 10 + 10 + 2 + 22 + 64 + 15 + 16 * (4 * 29 + 35) + 3,
+    # k_verify_hash besides Poseidon: two on-curve gates 10 + Montgomery conversions 6
+    "verify_hash_extra": 10 + 6,
+    # k_verify_ec (half-size scalars, 33 radix-16 windows over the tables of 8A and R8):
+    # conversions 4 + map 4 + 8A 22 + two 9-entry tables 2 x 64 + 32 x (3 x 7 + 8) doublings
+    # + 33 x (8 + 7) table additions + 1 + 17 B8 additions (16 x 7 + 6)
+    "verify_ec": 4 + 4 + 22 + 128 + 32 * 29 + 33 * 15 + 1 + 16 * 7 + 6,
     "fixed_base": 17 * 7 + 1 + 5 + 2 + 12,            # 16-bit comb + map + batched inversion share
     "mul_scalar": 2 + 5 + 2 + 64 + 7 + 64 * 36 + 20,  # gate, table, 64 windows x (4 dbl + add), batched inversion share
 }
 # Poseidon t = 6, sparse schedule: 8 full rounds x (6 x^5 + 6 dot6) + 60 partial x (x^5 + dot6 + 5 fmul)
 POSEIDON6_MAC = 8 * (6 * 3 * FMUL + 6 * (6 * 64 + 64)) + 60 * (3 * FMUL + (6 * 64 + 64) + 5 * FMUL)
+# k_verify_split: ~75 Euclid steps x (8 + 8) wide multiplies + two Montgomery products mod l
+SPLIT_MAC = 75 * 16 + 2 * FMUL
 ALGO_MAC = {
-    "verify": ALGO_FMUL["verify_ec"] * FMUL + POSEIDON6_MAC,
+    "verify": (ALGO_FMUL["verify_hash_extra"] + ALGO_FMUL["verify_ec"]) * FMUL + POSEIDON6_MAC + SPLIT_MAC,
     "fixed_base": ALGO_FMUL["fixed_base"] * FMUL,
     "mul_scalar": ALGO_FMUL["mul_scalar"] * FMUL,
 }
@@ -377,10 +382,13 @@ def run_ours(args, rank, local_rank, world):
         "algorithmic_mac_per_verify": ALGO_MAC["verify"],
         "frac_at_observed_clock": (achieved / (sms * WIDE_MAC_LANES_PER_CLK_SM * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_verify_ec) per launch, from the
-        # ncu --set full capture at this workload size (profiles/r1_ncu_verify_final_summary.txt): 431.2 MB per
-        # 2^21 lanes = 205.6 B per lane, against 193 B per lane algorithmic (192 B in, 1 B out)
-        "traffic": int(n * 205.6),
-        "dominant_kernel": "k_verify_ec (Straus pass): 92.9 ms of a 131 ms step; fmaheavy pipe 85.2 % busy (ncu)",
+        # ncu --set full capture at this workload size (profiles/r1_ncu_verify_split_summary.txt): 8.18 GB per
+        # 2^21 lanes = 3,899 B per lane, against 225 B per lane algorithmic (4 coordinates + 3 scalars in, 1 B
+        # out).  The excess is the per-thread window tables (2 x 9 x 128 B written, 66 x 128 B read per lane;
+        # 87 MB live, more than L2 keeps): 115 GB/s, under 2 % of HBM bandwidth -- not what bounds this kernel.
+        "traffic": int(n * 3899),
+        "dominant_kernel": "k_verify_ec (Straus pass over half-size scalars): ~71 ms of a 110 ms step; fmaheavy pipe "
+                           "78 % busy at 2^20 lanes, 66 % at 2^21 (ncu); k_verify_hash 33 ms, 92 % busy",
         "hbm": {"achieved_gbs": per_gpu * 193 / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind,
                 "note": "193 B per verify (6 x 32 B in, 1 B out); secondary counter, this path is not HBM-bound"},
     }
