@@ -414,10 +414,19 @@ BJJ_HD_NOINLINE void mul_scalar_exact(PointAff& r, const PointAff& p, const uint
     int nb = 0;     // BigInt::bits()
     for (int i = 0; i < nwords; i++)
         if (n[i]) nb = 32 * i + (32 - clz32(n[i]));
+    // The exact lanes are few and latency-bound (fewer than two such warps per SMSP), and in a warp the lanes'
+    // bits differ anyway: r + exp is computed every step next to exp + exp -- two independent dependency
+    // chains in one basic block -- and kept only where the bit is set.
 #pragma unroll 1
     for (int i = 0; i < nb; i++) {
-        if ((n[i >> 5] >> (i & 31)) & 1) proj_add_bbjlp(acc, acc, e);
-        proj_add_bbjlp(e, e, e);
+        const bool bit = (n[i >> 5] >> (i & 31)) & 1;
+        PointProj t, e2;
+        proj_add_bbjlp(t, acc, e);
+        proj_add_bbjlp(e2, e, e);
+        fr_cmov(acc.x, t.x, bit);
+        fr_cmov(acc.y, t.y, bit);
+        fr_cmov(acc.z, t.z, bit);
+        e = e2;
     }
     proj_affine(r, acc);
 }
