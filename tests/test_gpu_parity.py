@@ -173,6 +173,31 @@ def test_device_pointer_flavour_across_subbatches(gpu, oracle_c):
         idx = np.concatenate([np.arange(8), np.arange((1 << 21) - 4, (1 << 21) + 4), np.arange(n - 8, n)])
         ex, _ = oracle_c.public(keys[idx])
         assert np.array_equal(ax[idx], ex)
+        # the same signatures through the HOST flavour: ramped chunks (2^18, 2^19, 2^20, ...) on two copy streams,
+        # one compute stream, exact lanes (off-curve points below) joined at each chunk's copy-out
+        n2 = (1 << 20) + (1 << 18) + 333
+        host = {}
+        for name in ("r8x", "r8y", "s", "ay"):
+            host[name] = np.empty((n2, 32), dtype=np.uint8)
+            assert lib.bjj_memcpy_d2h(ctx, host[name].ctypes.data_as(ctypes.c_void_p), d[name], 32 * n2) == 0
+        eng.sync()
+        hax, hmsg = ax[:n2].copy(), msgs[:n2].copy()
+        bad = np.arange(100, n2, 4099)                   # spread over every chunk
+        for j, i in enumerate(bad):
+            if j % 3 == 0:
+                hax[i, 0] ^= 1                           # A off the curve (or another point): exact lane, rejects
+            elif j % 3 == 1:
+                host["r8x"][i, 0] ^= 1                   # R8 off the curve
+            else:
+                host["s"][i, 0] ^= 1                     # wrong S
+        ok2 = eng.verify_batch(host["r8x"], host["r8y"], host["s"], hax, host["ay"], hmsg)
+        exp2 = np.ones(n2, dtype=np.uint8)
+        exp2[5] = 0
+        exp2[bad] = 0
+        assert np.array_equal(ok2, exp2)
+        chk = np.concatenate([bad[:64], bad[-64:], np.arange(16)])
+        assert np.array_equal(ok2[chk], oracle_c.verify(host["r8x"][chk], host["r8y"][chk], host["s"][chk], hax[chk],
+                                                        host["ay"][chk], hmsg[chk]))
     finally:
         for p in list(d.values()) + [d_st, d_ok]:
             lib.bjj_dev_free(ctx, p)
