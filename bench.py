@@ -74,29 +74,65 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples SM clocks / throttle reasons of one GPU while the timed region runs: NVML in-process (a sample
+    every 20 ms, cheap enough for 8 ranks at once), `nvidia-smi -lms` as the fallback when pynvml is missing"""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, device):
         super().__init__(daemon=True)
         self.device = device
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, [reason names])
         self.stop_flag = threading.Event()
         self.proc = None
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.device < len(ids) and ids[self.device].isdigit():
+                return int(ids[self.device])
+        return self.device
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+        smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            mask = int(get_reasons(h))
+            self.rows.append((sm, smax, [nm for nm, bit in self.NVML_REASONS if mask & bit]))
+            time.sleep(0.02)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.rows.append((float(r[1]), float(r[2]), [nm for nm, v in zip(names, r[5:9]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
+            if self.stop_flag.is_set():
+                break
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-                if self.stop_flag.is_set():
-                    break
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
 
     def finish(self):
         self.stop_flag.set()
@@ -106,20 +142,12 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         self.join(timeout=2)
-        sm, smax, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                smax = max(smax, float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({nm for r in self.rows for nm in r[2]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons,
+                "samples": len(sm), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------------
