@@ -105,18 +105,6 @@ BJJ_HD void table_load(Niels& n, const LaneTable& t, int e) {
     }
 }
 
-// L1 prefetch of the entry a later table_select(t, d) / comb_select(comb, w, d) will read (no registers held)
-#if BJJ_DEVICE_CODE
-#define BJJ_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
-#else
-#define BJJ_PREFETCH_L1(ptr) ((void)(ptr))
-#endif
-BJJ_HD void table_prefetch(const LaneTable& t, int d) {
-    const int e = d < 0 ? -d : d;
-#pragma unroll
-    for (int q = 0; q < 8; q++) BJJ_PREFETCH_L1(t.base + (size_t)(e * 8 + q) * t.stride + t.slot);
-}
-
 // entries 0..8 = j*P
 BJJ_HD void table_build(const LaneTable& t, const PointExt& p) {
     Niels n, n1;
@@ -157,13 +145,6 @@ void bjj_emu_need_comb_entry(const struct CombEntry* comb, int w, int j);
 struct CombEntry {   // 96 bytes
     uint32_t ypx[8], ymx[8], t2d[8];
 };
-
-BJJ_HD void comb_prefetch(const CombEntry* comb, int w, int d) {
-    const int ad = d < 0 ? -d : d;
-    const uint8_t* e = reinterpret_cast<const uint8_t*>(comb + (size_t)w * BJJ_COMB_ENTRIES + ad);
-    BJJ_PREFETCH_L1(e);           // 96 bytes: at most two 128-byte lines
-    BJJ_PREFETCH_L1(e + 80);
-}
 
 BJJ_HD void comb_select(NielsAff& n, const CombEntry* comb, int w, int d) {
     int ad = d < 0 ? -d : d;
