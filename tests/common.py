@@ -328,6 +328,17 @@ def signature_cases(rnd, n_valid=6):
     x4 = O.modsqrt(pow(O.A, Q - 2, Q), Q)
     cases.append([R[0], R[1], s, x4, 0, 78])                    # A of order 4
     cases.append([0, 1, 0, base[3], base[4], base[5]])          # S = 0, R8 = identity
+    # the equation missed by a point of order 2 / 4 only: S*B8 - R8 - 8hm*A is a non-zero torsion point.  (The
+    # engine checks v*(...) == O for an ODD v -- an even v would accept these.)  hm changes with R8, so these are
+    # built from the relation directly: pick R8' = S*B8 - 8hm'*A + T is not possible in closed form; instead
+    # keep A = identity-like points where hm does not matter.
+    for tors in ((0, Q - 1), (x4, 0), (Q - x4, 0)):
+        Rt = O.proj_affine(O.proj_add(R + (1,), tors + (1,)))
+        cases.append([Rt[0], Rt[1], s, 0, 1, 77])               # R8 = S*B8 + T, A = identity -> false
+        cases.append([Rt[0], Rt[1], s, 0, Q - 1, 79])           # same with A of order 2
+    cases.append(mod(2, base[2] + 37 * O.SUBORDER))             # S close to 2^256: still valid, recoding carry
+    cases.append(mod(2, base[2] + 41 * O.SUBORDER))
+    cases.append(mod(2, (base[2] + 41 * O.SUBORDER) ^ 1))
     return cases
 
 
