@@ -746,9 +746,11 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
     if (n == 0) return BJJ_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t chunk = n < BJJ_CHUNK_LANES ? n : BJJ_CHUNK_LANES;
+    // a chunk may grow by half when the lanes left over after it would make a short, inefficient last chunk
+    const size_t cap = chunk + chunk / 2;
     // every array slice starts 256-byte aligned inside the arena
     size_t need = 0;
-    for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * chunk + 255) & ~(size_t)255);
+    for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
     int rc = BJJ_OK;
     int which = 0;
     size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
@@ -756,6 +758,7 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
     for (size_t off = 0; off < n; off += m, which ^= 1, cur = (2 * cur < chunk ? 2 * cur : chunk)) {
         PipeSlot& sl = ctx->slot[which];
         m = (n - off) < cur ? (n - off) : cur;
+        if (n - off - m < cur / 2 && n - off <= cap) m = n - off;      // fold a short remainder into this chunk
         if (sl.arena_bytes < need) {
             CU(ctx, cudaStreamSynchronize(sl.stream));
             if (sl.arena) cudaFree(sl.arena);
@@ -769,7 +772,7 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         size_t pos = 0;
         for (int a = 0; a < nargs; a++) {
             dptr[a] = sl.arena + pos;
-            pos += ((args[a].bytes_per_lane * chunk + 255) & ~(size_t)255);
+            pos += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
             if (args[a].in)
                 CU(ctx, cudaMemcpyAsync(dptr[a], args[a].in + off * args[a].bytes_per_lane, m * args[a].bytes_per_lane,
                                         cudaMemcpyHostToDevice, sl.stream));
