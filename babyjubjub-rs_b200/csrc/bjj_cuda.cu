@@ -177,7 +177,8 @@ static int ensure_table(bjj_ctx* ctx, Workspace* ws, size_t slots) {
 
 // makes room for two queues of n lane indices each and zeroes both counters on `st`
 static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, ExactQueue* q, ExactQueue* q2 = nullptr) {
-    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, 2 * sizeof(uint32_t)));
+    // 32 bytes: the two queue counters, then (at byte 16) the two lane-claim counters of the verify kernels
+    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, 32));
     if (ws->exact_cap < n) {
         if (ws->exact_list) cudaFree(ws->exact_list);
         ws->exact_list = nullptr;
@@ -185,7 +186,7 @@ static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, 
         CU(ctx, cudaMalloc(&ws->exact_list, 2 * n * sizeof(uint32_t)));
         ws->exact_cap = n;
     }
-    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, 2 * sizeof(uint32_t), st));
+    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, 32, st));
     q->count = ws->exact_count;
     q->list = ws->exact_list;
     if (q2) {
@@ -194,6 +195,8 @@ static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, 
     }
     return BJJ_OK;
 }
+
+static unsigned long long* work_counters(Workspace* ws) { return reinterpret_cast<unsigned long long*>(ws->exact_count + 4); }
 
 // sub-batch size of the point kernels: bounds the projective scratch at 4 x 32 B x 2^21 = 256 MiB
 #define BJJ_POINT_SUBBATCH ((size_t)1 << 21)
@@ -523,7 +526,7 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
             cudaEventRecord(pe[0], st);
         }
         bjjk::verify_hash(grid_h, st, m, r8x + o, r8y + o, ax + o, ay + o, msg + o, s + o, 1, 0, nullptr, hm, ws->vs_lanes, ok + off, true,
-                          qa, qr, ctx->flags_dev, mode, ctx->verify_split, msg_status ? msg_status + off : nullptr);
+                          qa, qr, ctx->flags_dev, mode, ctx->verify_split, msg_status ? msg_status + off : nullptr, work_counters(ws));
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         if (ctx->verify_split && mode == BJJ_MODE_EDDSA) {
@@ -536,7 +539,7 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         // (slow, rare) exact lanes follow on the side stream in single-warp CTAs that fit next to it.  All
         // three kernels write disjoint ok[] lanes.
         CU(ctx, cudaEventRecord(ws->ev_fork, st));
-        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, ax + o, ay + o, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, mode);
+        bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, ax + o, ay + o, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, mode, work_counters(ws) + 1);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
@@ -593,7 +596,7 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         ctx->launches += 5;
         CU(ctx, cudaGetLastError());
         bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, sig64 + 2 * o, 2, 1, status + off, hm, ws->vs_lanes, ok + off, false, q,
-                          q, ctx->flags_dev, BJJ_MODE_EDDSA, ctx->verify_split, nullptr);
+                          q, ctx->flags_dev, BJJ_MODE_EDDSA, ctx->verify_split, nullptr, work_counters(ws));
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         if (ctx->verify_split) {
@@ -601,7 +604,7 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
             ctx->launches++;
             CU(ctx, cudaGetLastError());
         }
-        bjjk::verify_ec(grid_e, st, m, dx, dy, dax, day, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, BJJ_MODE_EDDSA);
+        bjjk::verify_ec(grid_e, st, m, dx, dy, dax, day, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, BJJ_MODE_EDDSA, work_counters(ws) + 1);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
     }
@@ -753,6 +756,16 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
     for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
     int rc = BJJ_OK;
     int which = 0;
+    // BJJ_PIPE_TIMING=1: per-chunk timeline (ms since the call started) on stderr -- diagnosis only
+    static const bool pipe_timing = getenv("BJJ_PIPE_TIMING") != nullptr;
+    struct Mark { cudaEvent_t in, comp, out; size_t lanes; };
+    Mark marks[64];
+    int nmarks = 0;
+    cudaEvent_t t0 = nullptr;
+    if (pipe_timing) {
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, ctx->stream);
+    }
     size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
     size_t m = 0;
     for (size_t off = 0; off < n; off += m, which ^= 1, cur = (2 * cur < chunk ? 2 * cur : chunk)) {
@@ -779,9 +792,19 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         }
         ComputeRef comp{ctx->stream, which ? ctx->ws2 : ctx->ws};
         CU(ctx, cudaEventRecord(sl.ev_in, sl.stream));
+        const bool mark = pipe_timing && nmarks < 64;
+        if (mark) {
+            Mark& mk = marks[nmarks];
+            cudaEventCreate(&mk.in);
+            cudaEventCreate(&mk.comp);
+            cudaEventCreate(&mk.out);
+            mk.lanes = m;
+            cudaEventRecord(mk.in, sl.stream);
+        }
         CU(ctx, cudaStreamWaitEvent(comp.stream, sl.ev_in, 0));
         rc = launch(m, dptr, comp);
         if (rc) return rc;
+        if (mark) cudaEventRecord(marks[nmarks].comp, comp.stream);
         CU(ctx, cudaEventRecord(sl.ev_out, comp.stream));
         CU(ctx, cudaStreamWaitEvent(sl.stream, sl.ev_out, 0));
         if (comp.ws.aux) CU(ctx, cudaStreamWaitEvent(sl.stream, comp.ws.ev_join, 0));      // deferred exact lanes
@@ -789,8 +812,24 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
             if (args[a].out)
                 CU(ctx, cudaMemcpyAsync(args[a].out + off * args[a].bytes_per_lane, dptr[a], m * args[a].bytes_per_lane,
                                         cudaMemcpyDeviceToHost, sl.stream));
+        if (mark) cudaEventRecord(marks[nmarks++].out, sl.stream);
     }
-    return bjj_sync(ctx);
+    rc = bjj_sync(ctx);
+    if (pipe_timing) {
+        for (int k = 0; k < nmarks; k++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, t0, marks[k].in);
+            cudaEventElapsedTime(&b, t0, marks[k].comp);
+            cudaEventElapsedTime(&d, t0, marks[k].out);
+            fprintf(stderr, "[bjj pipe] chunk %d lanes=%zu copied-in at %.2f ms, kernels done at %.2f ms, copied-out at %.2f ms\n", k,
+                    marks[k].lanes, a, b, d);
+            cudaEventDestroy(marks[k].in);
+            cudaEventDestroy(marks[k].comp);
+            cudaEventDestroy(marks[k].out);
+        }
+        cudaEventDestroy(t0);
+    }
+    return rc;
 }
 
 #define H_IN(p, b) HostArg{(p), nullptr, (b)}

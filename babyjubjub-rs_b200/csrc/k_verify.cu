@@ -23,9 +23,11 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_verify_hash(
 #endif
     size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay, const uint8_t* msg,
     const uint8_t* s_base, size_t s_stride, size_t s_off, const uint8_t* skip, uint8_t* hm, size_t plane, uint8_t* ok,
-    int gate, ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode, int split, uint8_t* msg_status) {
+    int gate, ExactQueue qa, ExactQueue qr, uint32_t* gflags, int mode, int split, uint8_t* msg_status,
+    unsigned long long* work) {
     BJJ_FLAGS_BEGIN
-    BJJ_LANE_LOOP(n)
+    BJJ_CLAIM_LOOP(n, work)
+    if (i < n)
     lane_verify_hash(r8x, r8y, ax, ay, msg, s_base, s_stride, s_off, skip, hm, plane, ok, i, gate != 0, qa, qr, flags, mode,
                      split != 0, msg_status);
     BJJ_FLAGS_END(gflags)
@@ -44,11 +46,12 @@ __global__ void __launch_bounds__(BJJ_BLOCK, 4) k_verify_split(size_t n, const u
 __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                          size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
-                                                         int mode) {
+                                                         int mode, unsigned long long* work) {
     // two per-thread radix-16 tables (multiples of 8A and of R8), back to back
     const LaneTable tbl_a = thread_table(table);
     const LaneTable tbl_r = thread_table(table + (size_t)BJJ_TABLE_U128_PER_LANE * gridDim.x * blockDim.x);
-    BJJ_LANE_LOOP(n) lane_verify_ec(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode);
+    BJJ_CLAIM_LOOP(n, work)
+    if (i < n) lane_verify_ec(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode);
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
@@ -82,9 +85,9 @@ int verify_split_blocks_per_sm() { return occ((const void*)k_verify_split, BJJ_B
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* s_base, size_t s_stride, size_t s_off,
                  const uint8_t* skip, uint8_t* hm, size_t plane, uint8_t* ok, bool gate, ExactQueue qa, ExactQueue qr,
-                 uint32_t* gflags, int mode, bool split, uint8_t* msg_status) {
+                 uint32_t* gflags, int mode, bool split, uint8_t* msg_status, unsigned long long* work) {
     k_verify_hash<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, msg, s_base, s_stride, s_off, skip, hm, plane, ok, gate ? 1 : 0,
-                                              qa, qr, gflags, mode, split ? 1 : 0, msg_status);
+                                              qa, qr, gflags, mode, split ? 1 : 0, msg_status, work);
 }
 void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, size_t s_stride, size_t s_off, uint8_t* hm,
                   size_t plane, const uint8_t* ok) {
@@ -92,8 +95,8 @@ void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, si
 }
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                const uint8_t* ay, const uint8_t* hm, size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
-               int mode) {
-    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode);
+               int mode, unsigned long long* work) {
+    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode, work);
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb,

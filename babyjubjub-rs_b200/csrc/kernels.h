@@ -13,6 +13,18 @@
 
 #define BJJ_LANE_LOOP(n) \
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+// Dynamic lane assignment: a warp claims 32 consecutive lanes at a time from a device counter (zeroed before the
+// launch).  A CTA that becomes resident late -- the exact-lane kernel of the previous batch may still hold
+// registers on its SM -- then simply takes less work, where a grid-stride split would make the whole kernel
+// wait for it.
+#if defined(__CUDACC__)
+__device__ __forceinline__ size_t bjj_claim_lanes(unsigned long long* counter) {
+    unsigned long long b = 0;
+    if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 32ull);
+    return (size_t)__shfl_sync(0xFFFFFFFFu, b, 0) + (threadIdx.x & 31);
+}
+#endif
+#define BJJ_CLAIM_LOOP(n, counter) for (size_t i = bjj_claim_lanes(counter); i - (threadIdx.x & 31) < (n); i = bjj_claim_lanes(counter))
 #define BJJ_QUEUE_LOOP(q) \
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *(q).count; j < cnt; j += gridDim.x * blockDim.x)
 #define BJJ_FLAGS_BEGIN uint32_t flags = 0;
@@ -46,12 +58,12 @@ int poseidon_blocks_per_sm(int t);
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                  const uint8_t* ay, const uint8_t* msg, const uint8_t* s_base, size_t s_stride, size_t s_off,
                  const uint8_t* skip, uint8_t* hm, size_t plane, uint8_t* ok, bool gate, bjj::ExactQueue qa,
-                 bjj::ExactQueue qr, uint32_t* gflags, int mode, bool split, uint8_t* msg_status);
+                 bjj::ExactQueue qr, uint32_t* gflags, int mode, bool split, uint8_t* msg_status, unsigned long long* work);
 void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, size_t s_stride, size_t s_off, uint8_t* hm,
                   size_t plane, const uint8_t* ok);
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                const uint8_t* ay, const uint8_t* hm, size_t plane, uint8_t* ok, bjj::U128* table,
-               const bjj::CombEntry* comb, int mode);
+               const bjj::CombEntry* comb, int mode, unsigned long long* work);
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, bjj::ExactQueue qa, bjj::ExactQueue qr,
                   const bjj::CombEntry* comb, int mode);
