@@ -415,8 +415,8 @@ def run_ours(args, rank, local_rank, world):
         # out).  The excess is the per-thread window tables (2 x 9 x 128 B written, 66 x 128 B read per lane;
         # 87 MB live, more than L2 keeps): 115 GB/s, under 2 % of HBM bandwidth -- not what bounds this kernel.
         "traffic": int(n * 3899),
-        "dominant_kernel": "k_verify_ec (Straus pass over half-size scalars): ~71 ms of a 110 ms step; fmaheavy pipe "
-                           "78 % busy at 2^20 lanes, 66 % at 2^21 (ncu); k_verify_hash 33 ms, 92 % busy",
+        "dominant_kernel": "k_verify_ec (Straus pass over half-size scalars): 67 ms of a 105 ms step (BJJ_PHASE_TIMING); "
+                           "fmaheavy pipe 78 % busy at 2^20 lanes, 66 % at 2^21 under ncu; k_verify_hash 33 ms, 92 % busy",
         "hbm": {"achieved_gbs": per_gpu * 193 / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_kind": peak_kind,
                 "note": "193 B per verify (6 x 32 B in, 1 B out); secondary counter, this path is not HBM-bound"},
     }
