@@ -120,6 +120,17 @@ class Engine:
         self._check(self.lib.bjj_fr_op_batch(self.ctx, op, len(a), _ptr(a), _ptr(b), _ptr(out)), "bjj_fr_op_batch")
         return out
 
+    def split_scalars_batch(self, h, s):
+        """test hook: verify's half-size scalars; returns (u, |v|, v_is_negative, w) -- see include/bjj_cuda.h"""
+        h, s = _as_u8(h, 32), _as_u8(s, 32)
+        u, v, w = np.empty_like(h), np.empty_like(h), np.empty_like(h)
+        self._check(self.lib.bjj_split_scalars_batch(self.ctx, len(h), _ptr(h), _ptr(s), _ptr(u), _ptr(v), _ptr(w)),
+                    "bjj_split_scalars_batch")
+        neg = (v[:, 31] >> 7).astype(np.uint8)
+        v = v.copy()
+        v[:, 31] &= 0x7F
+        return u, v, neg, w
+
     def add_batch(self, px, py, pz, qx, qy, qz):
         ins = [_as_u8(v, 32) for v in (px, py, pz, qx, qy, qz)]
         outs = [np.empty_like(ins[0]) for _ in range(3)]

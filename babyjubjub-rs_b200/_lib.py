@@ -29,6 +29,7 @@ SIGNATURES = {
     "bjj_memcpy_h2d": (_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, _sz]),
     "bjj_memcpy_d2h": (_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, _sz]),
     "bjj_fr_op_batch": (_int, [_ctx, _int, _sz, _u8p, _u8p, _u8p]),
+    "bjj_split_scalars_batch": (_int, [_ctx, _sz] + [_u8p] * 5),
     "bjj_add_batch": (_int, [_ctx, _sz] + [_u8p] * 9),
     "bjj_affine_batch": (_int, [_ctx, _sz] + [_u8p] * 5),
     "bjj_mul_scalar_batch": (_int, [_ctx, _sz] + [_u8p] * 5),

@@ -28,6 +28,11 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_comb_build(CombEntry* comb) {
     comb_build_entry(comb, w, j);
 }
 
+__global__ void __launch_bounds__(BJJ_BLOCK) k_split_scalars(size_t n, const uint8_t* h32, const uint8_t* s32, uint8_t* u32,
+                                                             uint8_t* v32, uint8_t* w32) {
+    BJJ_LANE_LOOP(n) lane_split_scalars(h32, s32, u32, v32, w32, i);
+}
+
 __global__ void __launch_bounds__(BJJ_BLOCK) k_fr_op(int op, size_t n, const uint8_t* a, const uint8_t* b,
                                                      uint8_t* out, uint32_t* gflags) {
     BJJ_FLAGS_BEGIN
@@ -629,6 +634,14 @@ int bjj_fr_op_batch_dev(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const 
     DEV_EPILOGUE
 }
 
+int bjj_split_scalars_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* h32, const uint8_t* s32, uint8_t* u32,
+                                uint8_t* v32, uint8_t* w32, void* stream) {
+    DEV_PROLOGUE
+    if (!h32 || !s32 || !u32 || !v32 || !w32) return BJJ_ERR_ARG;
+    k_split_scalars<<<grid_for(ctx, (const void*)k_split_scalars, n), BJJ_BLOCK, 0, st>>>(n, h32, s32, u32, v32, w32);
+    DEV_EPILOGUE
+}
+
 int bjj_add_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz,
                       const uint8_t* qx, const uint8_t* qy, const uint8_t* qz, uint8_t* rx, uint8_t* ry, uint8_t* rz,
                       void* stream) {
@@ -847,6 +860,16 @@ int bjj_fr_op_batch(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint
     HostArg args[] = {H_IN(a, 32), H_IN(b, 32), H_OUT(out, 32)};
     return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         k_fr_op<<<grid_for(ctx, (const void*)k_fr_op, m), BJJ_BLOCK, 0, sl.stream>>>(op, m, d[0], d[1], d[2], ctx->flags_dev);
+        CHECK_LAUNCH(ctx)
+    });
+}
+
+int bjj_split_scalars_batch(bjj_ctx* ctx, size_t n, const uint8_t* h32, const uint8_t* s32, uint8_t* u32, uint8_t* v32,
+                            uint8_t* w32) {
+    if (!ctx) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(h32, 32), H_IN(s32, 32), H_OUT(u32, 32), H_OUT(v32, 32), H_OUT(w32, 32)};
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
+        k_split_scalars<<<grid_for(ctx, (const void*)k_split_scalars, m), BJJ_BLOCK, 0, sl.stream>>>(m, d[0], d[1], d[2], d[3], d[4]);
         CHECK_LAUNCH(ctx)
     });
 }

@@ -1064,6 +1064,19 @@ BJJ_HD void lane_verify_hash(const uint8_t* r8x, const uint8_t* r8y, const uint8
     store_u256(hm_out, 3 * plane + i, sv);
 }
 
+// test hook (bjj_split_scalars_batch): the split on caller-supplied h and s
+BJJ_HD void lane_split_scalars(const uint8_t* h32, const uint8_t* s32, uint8_t* u32, uint8_t* v32, uint8_t* w32, size_t i) {
+    uint32_t h[8], sv[8], u[8], v[8], w[8], vneg = 0;
+    load_u256(h, h32, i);
+    load_u256(sv, s32, i);
+    split_scalars(u, v, vneg, h);
+    split_scale_s(w, sv, v);
+    v[7] |= vneg << 31;
+    store_u256(u32, i, u);
+    store_u256(v32, i, v);
+    store_u256(w32, i, w);
+}
+
 // phase 1b (EdDSA): half-size scalars for the pending lanes (split.cuh).  Its own kernel: integer-ALU work with
 // lane-dependent trip counts, which inside the hash kernel would leave that kernel's warps out of step.
 BJJ_HD void lane_verify_split(const uint8_t* s_base, size_t s_stride, size_t s_off, uint8_t* hm_io, size_t plane,

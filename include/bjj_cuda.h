@@ -88,6 +88,15 @@ int bjj_memcpy_d2h(bjj_ctx* ctx, void* dst, const void* src, size_t bytes);   /*
 int bjj_fr_op_batch(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
 int bjj_fr_op_batch_dev(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, void* stream);
 
+/* ---- verify's half-size scalars (no reference counterpart; csrc/split.cuh) -- test hook ---------
+ * For every 256-bit h and s:  u = v*h (mod SUBORDER), v odd and non-zero, w = |v|*s (mod SUBORDER).
+ * v32 holds |v| with the sign of v in bit 255.  Lets the parity suite drive the device code with crafted h
+ * (verify itself only ever sees Poseidon outputs). */
+int bjj_split_scalars_batch(bjj_ctx* ctx, size_t n, const uint8_t* h32, const uint8_t* s32, uint8_t* u32, uint8_t* v32,
+                            uint8_t* w32);
+int bjj_split_scalars_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* h32, const uint8_t* s32, uint8_t* u32,
+                                uint8_t* v32, uint8_t* w32, void* stream);
+
 /* ---- PointProjective::add (src/lib.rs:88-131): literal add-2008-bbjlp, projective in and out ---- */
 int bjj_add_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* pz,
                   const uint8_t* qx, const uint8_t* qy, const uint8_t* qz, uint8_t* rx, uint8_t* ry, uint8_t* rz);

@@ -34,6 +34,8 @@ extern "C" {
 
     // Fr ops (src/lib.rs:7) -- test hook
     pub fn bjj_fr_op_batch(ctx: *mut bjj_ctx, op: c_int, n: usize, a: *const u8, b: *const u8, out: *mut u8) -> c_int;
+    pub fn bjj_split_scalars_batch(ctx: *mut bjj_ctx, n: usize, h32: *const u8, s32: *const u8, u32_: *mut u8, v32: *mut u8,
+                                   w32: *mut u8) -> c_int;
     // PointProjective::add (src/lib.rs:88-131)
     pub fn bjj_add_batch(ctx: *mut bjj_ctx, n: usize, px: *const u8, py: *const u8, pz: *const u8, qx: *const u8,
                          qy: *const u8, qz: *const u8, rx: *mut u8, ry: *mut u8, rz: *mut u8) -> c_int;

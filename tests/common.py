@@ -349,3 +349,38 @@ def cases_to_arrays(cases):
 
 def oracle_verify(c):
     return int(O.verify((c[3], c[4]), ((c[0], c[1]), c[2]), c[5]))
+
+
+SUBORDER_L = O.SUBORDER
+
+
+def split_scalar_inputs(seed=77, n_random=400):
+    """h values for verify's scalar split (csrc/split.cuh): degenerate lattices, large partial quotients, every
+    operand length, and random field elements; returns (hs, ss)"""
+    L = SUBORDER_L
+    rnd = random.Random(seed)
+    hs = [0, 1, 2, 3, L - 1, L, L + 1, 2 * L, 7 * L, (L + 1) // 2, (L - 1) // 2, (L + 1) // 2 + 1, Q - 1, 2**256 - 1,
+          2**126, 2**127, 2**128 + 1, L // 3, 2 * L // 3, (1 << 200) + 1]
+    hs += [pow(2, k, L) for k in (125, 126, 127, 250)]
+    hs += [(L + 1) // 2 * k % L for k in (3, 5, 7)]           # 2h = k: short vectors with an even cofactor
+    hs += [(L * pn // qn + d) % (1 << 256) for qn in (2, 3, 5, 7, 64, 1 << 20, (1 << 40) + 1) for pn in (1, qn - 1) for d in (0, 1)]
+    hs += [L // k for k in (2, 3, 4, 1 << 31, 1 << 32, (1 << 32) + 1, 1 << 64, 1 << 125, 1 << 126, 1 << 127)]
+    hs += [rnd.randrange(1 << b) for b in (8, 31, 32, 33, 64, 100, 125, 126, 127, 128, 129, 160, 192, 224, 250, 251, 252, 254, 256)]
+    hs += [rnd.randrange(Q) for _ in range(n_random)]
+    ss = [rnd.randrange(1 << 256) for _ in hs]
+    ss[0], ss[1], ss[2] = 0, 2**256 - 1, L
+    return hs, ss
+
+
+def check_split_outputs(hs, ss, us, vs, negs, ws, max_wide=90):
+    """the invariants that make the split exact: u = v*h (mod l), v odd and non-zero, w = |v|*s (mod l)"""
+    L = SUBORDER_L
+    wide = 0
+    for h, s, u, v, ng, w in zip(hs, ss, us, vs, negs, ws):
+        sv = -v if ng else v
+        assert v % 2 == 1 and 0 < v < L, (h, v)
+        assert (sv * h - u) % L == 0, (h, u, sv)
+        assert (w - v * s) % L == 0 and w < 2 * L, (h, w)
+        if max(u, v) >= 0x70000000 << 96:
+            wide += 1
+    assert wide <= max_wide, wide      # only crafted degenerate inputs (+ a few random ones by a bit) exceed 32 windows

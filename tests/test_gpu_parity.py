@@ -323,3 +323,21 @@ def test_abi_argument_errors_and_context_lifecycle(gpu):
 
 def test_schnorr(gpu, oracle_c):
     parity.check_schnorr(gpu, oracle_c, 64)
+
+
+def test_split_scalars_on_device(gpu, hostemu):
+    """the device code of verify's scalar split on crafted h (degenerate lattices, whole-limb quotients, every
+    length) -- inputs verify itself never produces: the relation holds exactly and the device agrees with the
+    host build of the same header bit for bit"""
+    import ctypes
+    from common import check_split_outputs, split_scalar_inputs
+    hs, ss = split_scalar_inputs(n_random=4000)
+    H, S = pack(hs), pack(ss)
+    u, v, neg, w = gpu.eng.split_scalars_batch(H, S)
+    check_split_outputs(hs, ss, unpack(u), unpack(v), neg, unpack(w), max_wide=400)
+    n = len(hs)
+    U, V, W = np.zeros_like(H), np.zeros_like(H), np.zeros_like(H)
+    neg_h = np.zeros(n, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    hostemu.lib.emu_split(ctypes.c_size_t(n), p(H), p(S), p(U), p(V), p(neg_h), p(W))
+    assert np.array_equal(u, U) and np.array_equal(v, V) and np.array_equal(neg, neg_h) and np.array_equal(w, W)

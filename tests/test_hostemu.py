@@ -52,33 +52,15 @@ def test_split_scalars(hostemu):
     """verify's half-size scalars (csrc/split.cuh): u = v*h (mod l) exactly, v odd and non-zero, w = |v|*S (mod l);
     generic inputs give 127-bit scalars, degenerate lattices only longer ones."""
     import ctypes
-    import random
 
     import numpy as np
 
-    from common import Q, pack, unpack
-    L = 21888242871839275222246405745257275088614511777268538073601725287587578984328 >> 3
-    rnd = random.Random(77)
-    hs = [0, 1, 2, 3, L - 1, L, L + 1, 2 * L, 7 * L, (L + 1) // 2, (L - 1) // 2, (L + 1) // 2 + 1, Q - 1, 2**256 - 1,
-          2**126, 2**127, 2**128 + 1, L // 3, 2 * L // 3, (1 << 200) + 1]
-    hs += [pow(2, k, L) for k in (125, 126, 127, 250)]
-    hs += [(L + 1) // 2 * k % L for k in (3, 5, 7)]           # 2h = k: short vectors with an even cofactor
-    hs += [rnd.randrange(Q) for _ in range(400)]
-    ss = [rnd.randrange(1 << 256) for _ in hs]
-    ss[0], ss[1], ss[2] = 0, 2**256 - 1, L
+    from common import check_split_outputs, pack, split_scalar_inputs, unpack
+    hs, ss = split_scalar_inputs()
     n = len(hs)
     H, S = pack(hs), pack(ss)
     U, V, W = np.zeros_like(H), np.zeros_like(H), np.zeros_like(H)
     neg = np.zeros(n, dtype=np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     hostemu.lib.emu_split(ctypes.c_size_t(n), p(H), p(S), p(U), p(V), p(neg), p(W))
-    wide = 0
-    for h, s, u, v, w, ng in zip(hs, ss, unpack(U), unpack(V), unpack(W), neg):
-        sv = -v if ng else v
-        assert v % 2 == 1 and 0 < v < L, (h, v)
-        assert (sv * h - u) % L == 0, (h, u, sv)
-        assert (w - v * s) % L == 0 and w < 2 * L, (h, w)
-        if max(u, v) >= 0x70000000 << 96:
-            wide += 1
-    # only the crafted degenerate inputs may need more than 32 windows (+ a few random ones by a bit)
-    assert wide <= 40, wide
+    check_split_outputs(hs, ss, unpack(U), unpack(V), neg, unpack(W))
