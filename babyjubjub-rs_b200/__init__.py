@@ -340,6 +340,29 @@ def _sign(self, msg):
 PrivateKey.sign = _sign
 
 
+def _sign_schnorr(self, m, k=None):
+    """PrivateKey::sign_schnorr, src/lib.rs:345-362: k = 1024 random bits, r = B8*k, h = schnorr_hash(pk, m, r),
+    s = k + scalar_key*h (NOT reduced, like the reference).  Host glue around one fixed-base multiplication and
+    one Poseidon hash; B8 has order SUBORDER, so k crosses the 256-bit ABI reduced.  `k` may be supplied for
+    reproducible tests."""
+    import secrets
+    k = secrets.randbits(1024) if k is None else int(k)
+    rx, ry = default_engine().fixed_base_batch(ints_to_le32([k % SUBORDER]))
+    r = Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0])
+    h = schnorr_hash(self.public(), m, r)
+    return r, k + self.scalar_key() * h
+
+
+PrivateKey.sign_schnorr = _sign_schnorr
+
+
+def new_key():
+    """src/lib.rs:387-393: a private key from 32 random bytes (the reference draws a 1024-bit integer and keeps its
+    first 32 big-endian bytes)"""
+    import secrets
+    return PrivateKey(secrets.token_bytes(32))
+
+
 def verify(pk, sig, msg):
     """src/lib.rs:395-412"""
     msg = int(msg)

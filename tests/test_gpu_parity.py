@@ -81,6 +81,15 @@ def test_reference_api_mirror(gpu):
     assert bjj.public_batch([sk])[0].equals(pk)
     d = bjj.decompress_batch([c, (1).to_bytes(32, "little")])
     assert d[0].equals(p) and isinstance(d[1], ValueError)
+    k = (1 << 1023) + 0xDEADBEEF                                                      # test_schnorr_signature
+    r_s, s_s = sk.sign_schnorr(MSG_KAT, k=k)
+    o_r, o_s = O.sign_schnorr(KEY_KAT, MSG_KAT, k)
+    assert (r_s.x, r_s.y, s_s) == (o_r[0], o_r[1], o_s)
+    assert bjj.verify_schnorr(pk, MSG_KAT, r_s, s_s) is True
+    assert bjj.verify_schnorr(pk, MSG_KAT + 1, r_s, s_s) is False
+    sk2 = bjj.new_key()
+    r2, s2 = sk2.sign_schnorr(12345)
+    assert bjj.verify_schnorr(sk2.public(), 12345, r2, s2) is True
 
 
 def test_noncanonical_inputs_are_flagged(gpu):
