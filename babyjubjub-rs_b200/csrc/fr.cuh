@@ -295,7 +295,28 @@ BJJ_HD void fr_mul_inline(Fr& r, const Fr& a, const Fr& b) {
 
 // (An out-of-line multiplier -- one copy per kernel, 50x less code -- was measured and rejected: 22.5 vs
 // 26.1 M mults/s in k_mul_scalar; inlining lets ptxas interleave independent multiplications.)
+// BJJ_FR_MUL_CALL (experiment, off by default; tools/ab_verify.py): the multiplication as ONE out-of-line
+// subroutine per kernel, operands and result by value so that they travel in registers.  Trades call overhead
+// and the scheduler's overlap across multiplications for an instruction footprint of a few KB instead of ~3 KB
+// per multiplication site (the Straus kernel is instruction-supply bound).
+#if defined(BJJ_FR_MUL_CALL) && BJJ_DEVICE_CODE
+struct FrPair {
+    Fr a, b;
+};
+static __device__ __noinline__ Fr fr_mul_call(FrPair p) {
+    Fr r;
+    fr_mul_inline(r, p.a, p.b);
+    return r;
+}
+BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) {
+    FrPair p;
+    p.a = a;
+    p.b = b;
+    r = fr_mul_call(p);
+}
+#else
 BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) { fr_mul_inline(r, a, b); }
+#endif
 
 // One step of a Montgomery dot product  sum_p A_p * B_p  at column I (see fr_dot).
 #define BJJ_DOT_STEP(S, N, I, FOLD)                                                                   \
