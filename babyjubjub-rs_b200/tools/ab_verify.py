@@ -13,7 +13,7 @@ compared inside one gpurun call.  This tool
     python babyjubjub-rs_b200/tools/ab_verify.py build base: sqr:BJJ_DEDICATED_SQR=1
     gpurun --timeout 600 -- 'python babyjubjub-rs_b200/tools/ab_verify.py run base sqr'
 
-Nothing here is on the product path.
+AB_SKIP_TESTS=1 skips the parity tests, AB_STEPS=n sets the timed steps.  Nothing here is on the product path.
 """
 import os
 import shutil
@@ -54,16 +54,17 @@ def build(specs):
         print("built %-12s %-40s k_verify_ec %s" % (name, " ".join(defs) or "(no macros)", regs[0] if regs else "?"))
 
 
-def run(names, steps=3):
+def run(names, steps=int(os.environ.get("AB_STEPS", "3"))):
     keep = LIB + ".ab_keep"
     shutil.copy2(LIB, keep)
     try:
         for name in names:
             shutil.copy2(os.path.join(OUT, name, "libbjj_cuda.so"), LIB)
             print("== variant %s" % name, flush=True)
-            t = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-x", "-q", "-k", "verify or schnorr"],
-                               cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            print(t.stdout.strip().splitlines()[-1], flush=True)
+            if not os.environ.get("AB_SKIP_TESTS"):
+                t = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-x", "-q", "-k", "verify or schnorr"],
+                                   cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                print(t.stdout.strip().splitlines()[-1], flush=True)
             env = dict(os.environ, BJJ_PHASE_TIMING="1")
             p = subprocess.run([sys.executable, "bench.py", "--steps", str(steps), "--warmup", "3", "--no-secondary", "--cpu-seconds", "1"],
                                cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
