@@ -1,8 +1,8 @@
 """Builds libbjj_cuda.so for sm_100a with nvcc (in-tree, so the .so travels to the GPU box).
 
 One object per translation unit, compiled in parallel (the heavy kernels are minutes of ptxas each),
-then linked into babyjubjub-rs_b200/libbjj_cuda.so.  The measurement tools (csrc/imad_bench.cu,
-csrc/pipe_probe.cu) are built into babyjubjub-rs_b200/bin/.
+then linked into babyjubjub-rs_b200/libbjj_cuda.so.  The measurement tools (tools/microbench/*.cu)
+are built into babyjubjub-rs_b200/bin/; they are not part of the library.
 """
 import os
 import subprocess
@@ -16,7 +16,8 @@ BIN = os.path.join(HERE, "bin")
 GEN = os.path.join(CSRC, "generated", "bjj_consts.inc")
 LIB = os.path.join(HERE, "libbjj_cuda.so")
 LIB_UNITS = ["bjj_cuda.cu", "k_verify.cu", "k_mulscalar.cu", "k_sign.cu", "k_poseidon.cu"]
-TOOLS = ["imad_bench.cu", "pipe_probe.cu"]
+MB = os.path.join(HERE, "tools", "microbench")
+TOOLS = ["imad_bench.cu", "pipe_probe.cu", "fr_layouts.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "20091"]
 
@@ -67,10 +68,11 @@ def build(force=False, verbose=False, tools=True):
             jobs.append(cmd)
     if tools:
         for unit in TOOLS:
-            src = os.path.join(CSRC, unit)
+            src = os.path.join(MB, unit)
             exe = os.path.join(BIN, unit[:-3])
-            if force or _stale(exe, [src] + hdrs):
-                jobs.append([nvcc] + COMMON + ["-o", exe, src])
+            mb_hdrs = [os.path.join(MB, f) for f in os.listdir(MB) if f.endswith(".cuh")]
+            if force or _stale(exe, [src] + hdrs + mb_hdrs):
+                jobs.append([nvcc] + COMMON + ["-I", CSRC, "-o", exe, src])
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
             list(ex.map(lambda c: _run(c, logs), jobs))

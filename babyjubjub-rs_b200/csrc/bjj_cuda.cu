@@ -513,16 +513,17 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
         int rc = ensure_table(ctx, ws, 2 * (size_t)grid_e * BJJ_BLOCK);     // two per-thread tables: 8A and R8
         if (rc) return rc;
+        rc = ensure_aux(ctx, ws);
+        if (rc) return rc;
+        // exact lanes of an earlier batch may still be reading this workspace's queues and scratch (deferred join):
+        // wait for them BEFORE the queue counters are cleared and the scratch is reused
+        CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
         ExactQueue qa, qr;
         rc = ensure_queue(ctx, ws, m, st, &qa, &qr);
         if (rc) return rc;
         uint8_t *hm, *pts;
         rc = ensure_vscratch(ctx, ws, n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &hm, &pts);
         if (rc) return rc;
-        rc = ensure_aux(ctx, ws);
-        if (rc) return rc;
-        // exact lanes of an earlier batch may still be reading this workspace's scratch (deferred join)
-        CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
         // BJJ_PHASE_TIMING=1: synchronous per-phase CUDA-event timings on stderr (diagnosis only)
         static const bool phase_timing = getenv("BJJ_PHASE_TIMING") != nullptr;
         cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -579,6 +580,9 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         const int grid_e = grid_cap(ctx, bjjk::verify_ec_blocks_per_sm(), m);
         int rc = ensure_table(ctx, ws, 2 * (size_t)grid_e * BJJ_BLOCK);
         if (rc) return rc;
+        rc = ensure_aux(ctx, ws);
+        if (rc) return rc;
+        CU(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));      // a deferred exact kernel of an earlier verify on this workspace
         ExactQueue q;     // never fed here (decompressed points are on the curve) but the kernel wants a valid one
         rc = ensure_queue(ctx, ws, 1, st, &q);
         if (rc) return rc;

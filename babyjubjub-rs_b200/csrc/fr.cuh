@@ -240,6 +240,21 @@ BJJ_HD bool fr_eq(const Fr& a, const Fr& b) {
 // Montgomery multiplication
 // ------------------------------------------------------------------------------------------------
 
+// m = t * (-Q^-1 mod 2^32).  Q = 1 - 2^28 (mod 2^32), so -Q^-1 = -(1 + 2^28) and the product is a shift, an add and a
+// negation on the ALU pipe: the multiplier pipe, which bounds every kernel here, keeps its slots for the wide MACs
+// (8 IMAD less per multiplication, 3 % of its multiplier-pipe time).
+BJJ_HD uint32_t mont_m(uint32_t t) {
+    static_assert(BJJ_NINV32 == 0xefffffffu, "mont_m is specialised for Q = 0xf0000001 (mod 2^32)");
+#if BJJ_DEVICE_CODE
+    uint32_t s, m;
+    asm("shf.l.clamp.b32 %0, 0, %1, 28;" : "=r"(s) : "r"(t));      // t << 28 as a funnel shift (SHF: ALU pipe)
+    asm("sub.u32 %0, 0, %1;\n\tsub.u32 %0, %0, %2;" : "=r"(m) : "r"(s), "r"(t));
+    return m;
+#else
+    return 0u - (t + (t << 28));
+#endif
+}
+
 // One interleaved CIOS step at absolute column I.  S is the accumulator whose chain starts at column
 // I (X when I is even, Y when I is odd), N the other one.  FOLD: carry of column I-1 enters the chain.
 //
@@ -250,7 +265,7 @@ BJJ_HD bool fr_eq(const Fr& a, const Fr& b) {
     {                                                                                                   \
         mac4<FOLD, 1>(&S[I], a.v[0], a.v[2], a.v[4], a.v[6], b.v[I], X[(I) ? (I)-1 : 0], Y[(I) ? (I)-1 : 0]); \
         mac4<false, 0>(&N[I + 1], a.v[1], a.v[3], a.v[5], a.v[7], b.v[I]);                              \
-        uint32_t m = (S[I] + N[I]) * BJJ_NINV32;                                                        \
+        uint32_t m = mont_m(S[I] + N[I]);                                                        \
         mac4<false, 1>(&S[I], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);                                       \
         mac4<false, 0>(&N[I + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);                                   \
     }
@@ -293,31 +308,10 @@ BJJ_HD void fr_mul_inline(Fr& r, const Fr& a, const Fr& b) {
     fr_merge_xy(r, X, Y);
 }
 
-// (An out-of-line multiplier -- one copy per kernel, 50x less code -- was measured and rejected: 22.5 vs
-// 26.1 M mults/s in k_mul_scalar; inlining lets ptxas interleave independent multiplications.)
-// BJJ_FR_MUL_CALL (experiment, off by default; tools/ab_verify.py): the multiplication as ONE out-of-line
-// subroutine per kernel, operands and result by value so that they travel in registers.  Trades call overhead
-// and the scheduler's overlap across multiplications for an instruction footprint of a few KB instead of ~3 KB
-// per multiplication site (the Straus kernel is instruction-supply bound).  Measured on one
-// GPU against the inline build: k_verify_ec 67.7 vs 65.9-69.6 ms (no difference), k_verify_hash 37.9 vs 35.0 ms.
-#if defined(BJJ_FR_MUL_CALL) && BJJ_DEVICE_CODE
-struct FrPair {
-    Fr a, b;
-};
-static __device__ __noinline__ Fr fr_mul_call(FrPair p) {
-    Fr r;
-    fr_mul_inline(r, p.a, p.b);
-    return r;
-}
-BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) {
-    FrPair p;
-    p.a = a;
-    p.b = b;
-    r = fr_mul_call(p);
-}
-#else
+// (An out-of-line multiplier called with operands BY VALUE was measured twice and rejected: ~45 register moves per
+// call, 22.5 vs 26.1 M mults/s in k_mul_scalar, no gain in k_verify_ec.  Out-of-line multiplication with operands
+// in SHARED memory is a different design: see vm.cuh.)
 BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) { fr_mul_inline(r, a, b); }
-#endif
 
 // One step of a Montgomery dot product  sum_p A_p * B_p  at column I (see fr_dot).
 #define BJJ_DOT_STEP(S, N, I, FOLD)                                                                   \
@@ -329,7 +323,7 @@ BJJ_HD void fr_mul(Fr& r, const Fr& a, const Fr& b) { fr_mul_inline(r, a, b); }
                 mac4<false, 2>(&S[I], A[p].v[0], A[p].v[2], A[p].v[4], A[p].v[6], B[p].v[I]);           \
             mac4<false, 1>(&N[I + 1], A[p].v[1], A[p].v[3], A[p].v[5], A[p].v[7], B[p].v[I]);           \
         }                                                                                               \
-        uint32_t m = (S[I] + N[I]) * BJJ_NINV32;                                                        \
+        uint32_t m = mont_m(S[I] + N[I]);                                                        \
         mac4<false, 2>(&S[I], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);                                       \
         mac4<false, 1>(&N[I + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);                                   \
     }
@@ -357,149 +351,9 @@ BJJ_HD void fr_dot(Fr& r, const Fr* A, const Fr* B) {
     if (NP > 7) fr_cond_sub_2q(r);
 }
 
-// ------------------------------------------------------------------------------------------------
-// dedicated squaring: 28 cross products (doubled by a 1-bit shift) + 8 squares + 64 reduction MACs
-// = 100 wide MACs instead of 128
-// ------------------------------------------------------------------------------------------------
-
-// c[0..2N-1] += {a0..a(N-1)} * b (lo -> c[2k], hi -> c[2k+1]); carry-out added into c[2N].
-template <int N>
-BJJ_HD void macn(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
-#if BJJ_DEVICE_CODE
-    if (N == 1) {
-        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
-            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]) : "r"(a0), "r"(b));
-    } else if (N == 2) {
-        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\t"
-            "madc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\taddc.u32 %4, %4, 0;"
-            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]) : "r"(a0), "r"(a1), "r"(b));
-    } else if (N == 3) {
-        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\tmadc.hi.cc.u32 %1, %7, %10, %1;\n\t"
-            "madc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"
-            "madc.lo.cc.u32 %4, %9, %10, %4;\n\tmadc.hi.cc.u32 %5, %9, %10, %5;\n\taddc.u32 %6, %6, 0;"
-            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6])
-            : "r"(a0), "r"(a1), "r"(a2), "r"(b));
-    } else {
-        mac4<false, 1>(c, a0, a1, a2, a3, b);
-    }
-#else
-    const uint32_t a[4] = {a0, a1, a2, a3};
-    uint64_t carry = 0;
-    for (int k = 0; k < N; k++) {
-        uint64_t p = (uint64_t)a[k] * b;
-        uint64_t t = (uint64_t)c[2 * k] + (uint32_t)p + carry;
-        c[2 * k] = (uint32_t)t;
-        carry = t >> 32;
-        t = (uint64_t)c[2 * k + 1] + (p >> 32) + carry;
-        c[2 * k + 1] = (uint32_t)t;
-        carry = t >> 32;
-    }
-    c[2 * N] += (uint32_t)carry;
-#endif
-}
-
-// Montgomery reduction of a 512-bit value T (16 limbs, T < 2^256 * 1.2 Q):  r = T / 2^256 mod Q, r < 2Q.
-// redc(T) = mont_mul(T_lo, 1) + T_hi: the accumulators start as (X, Y) = (T_lo, 0) and run the eight
-// reduction-only steps of fr_mul (same column bounds: every chain top lands in an empty column); the
-// upper half of T is added once at the end.
-BJJ_HD void fr_redc16(Fr& r, const uint32_t* T) {
-    uint32_t X[18], Y[18];
-#pragma unroll
-    for (int i = 0; i < 18; i++) {
-        X[i] = i < 8 ? T[i] : 0;
-        Y[i] = 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t* S = (i & 1) ? Y : X;                 // chain that starts at column i
-        uint32_t* N = (i & 1) ? X : Y;
-        // carry of column i-1: X[i-1] + Y[i-1] is 0 or 2^32
-        const uint32_t c = i ? (((X[i ? i - 1 : 0] | Y[i ? i - 1 : 0]) != 0) ? 1u : 0u) : 0u;
-        const uint32_t m = (S[i] + N[i] + c) * BJJ_NINV32;
-        if (i == 0)
-            mac4<false, 1>(&S[i], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m);
-        else
-            mac4<true, 1>(&S[i], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m, X[i ? i - 1 : 0], Y[i ? i - 1 : 0]);
-        mac4<false, 0>(&N[i + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);
-    }
-    Fr u;
-    fr_merge_xy(u, X, Y);
-    add256(r.v, u.v, T + 8);
-}
-
-BJJ_HD void fr_sqr_dedicated(Fr& r, const Fr& a) {
-    uint32_t X[18], Y[18];
-#pragma unroll
-    for (int i = 0; i < 18; i++) X[i] = Y[i] = 0;
-    // cross products a_i * a_j (i < j): (i + j) odd -> Y, even -> X; see the column audit in DESIGN.md
-    macn<4>(&Y[1], a.v[1], a.v[3], a.v[5], a.v[7], a.v[0]);
-    macn<3>(&X[2], a.v[2], a.v[4], a.v[6], 0, a.v[0]);
-    macn<3>(&Y[3], a.v[2], a.v[4], a.v[6], 0, a.v[1]);
-    macn<3>(&X[4], a.v[3], a.v[5], a.v[7], 0, a.v[1]);
-    macn<3>(&Y[5], a.v[3], a.v[5], a.v[7], 0, a.v[2]);
-    macn<2>(&X[6], a.v[4], a.v[6], 0, 0, a.v[2]);
-    macn<2>(&Y[7], a.v[4], a.v[6], 0, 0, a.v[3]);
-    macn<2>(&X[8], a.v[5], a.v[7], 0, 0, a.v[3]);
-    macn<2>(&Y[9], a.v[5], a.v[7], 0, 0, a.v[4]);
-    macn<1>(&X[10], a.v[6], 0, 0, 0, a.v[4]);
-    macn<1>(&Y[11], a.v[6], 0, 0, 0, a.v[5]);
-    macn<1>(&X[12], a.v[7], 0, 0, 0, a.v[5]);
-    macn<1>(&Y[13], a.v[7], 0, 0, 0, a.v[6]);
-    // Z = X + Y (columns 0..15), then doubled, then the squares a_i^2 at columns 2i, 2i+1
-    uint32_t T[16];
-    {
-        uint32_t cin[8], hi[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) cin[i] = 0;
-        cin[0] = add256(T, X, Y);          // lower half; its carry enters the upper half
-        add256(hi, X + 8, Y + 8);
-        add256(T + 8, hi, cin);
-    }
-#pragma unroll
-    for (int i = 15; i > 0; i--) T[i] = (T[i] << 1) | (T[i - 1] >> 31);
-    T[0] <<= 1;
-#if BJJ_DEVICE_CODE
-    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\tmadc.hi.cc.u32 %1, %16, %16, %1;\n\t"
-        "madc.lo.cc.u32 %2, %17, %17, %2;\n\tmadc.hi.cc.u32 %3, %17, %17, %3;\n\t"
-        "madc.lo.cc.u32 %4, %18, %18, %4;\n\tmadc.hi.cc.u32 %5, %18, %18, %5;\n\t"
-        "madc.lo.cc.u32 %6, %19, %19, %6;\n\tmadc.hi.cc.u32 %7, %19, %19, %7;\n\t"
-        "madc.lo.cc.u32 %8, %20, %20, %8;\n\tmadc.hi.cc.u32 %9, %20, %20, %9;\n\t"
-        "madc.lo.cc.u32 %10, %21, %21, %10;\n\tmadc.hi.cc.u32 %11, %21, %21, %11;\n\t"
-        "madc.lo.cc.u32 %12, %22, %22, %12;\n\tmadc.hi.cc.u32 %13, %22, %22, %13;\n\t"
-        "madc.lo.cc.u32 %14, %23, %23, %14;\n\tmadc.hi.u32 %15, %23, %23, %15;"
-        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]),
-          "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
-        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
-#else
-    {
-        uint64_t carry = 0;
-        for (int i = 0; i < 8; i++) {
-            uint64_t p = (uint64_t)a.v[i] * a.v[i];
-            uint64_t t = (uint64_t)T[2 * i] + (uint32_t)p + carry;
-            T[2 * i] = (uint32_t)t;
-            carry = t >> 32;
-            t = (uint64_t)T[2 * i + 1] + (p >> 32) + carry;
-            T[2 * i + 1] = (uint32_t)t;
-            carry = t >> 32;
-        }
-    }
-#endif
-    fr_redc16(r, T);
-}
-
-// Measured on B200 (profiles/r1_imad_bench.jsonl): the dedicated squaring saves 28 of 128 IMAD.WIDE but
-// ptxas spends the difference on carry-flag traffic (P2R / IMAD.X / IMAD.MOV on the same fma pipe), so
-// it is not faster than fr_mul(a, a): v2 (single-chain redc) reaches 70-75 vs 68.3 G/s in isolation but costs registers: in k_verify_hash / k_verify_ec it was a net loss (13.1 vs 13.9 M verifies/s).  Kept selectable.
-#ifndef BJJ_DEDICATED_SQR
-#define BJJ_DEDICATED_SQR 0
-#endif
-BJJ_HD void fr_sqr(Fr& r, const Fr& a) {
-#if BJJ_DEDICATED_SQR
-    fr_sqr_dedicated(r, a);
-#else
-    fr_mul(r, a, a);
-#endif
-}
+// A dedicated squaring (28 doubled cross products + 8 squares + reduction = 100 wide MACs instead of 128) was
+// measured as a loss inside the kernels (tools/microbench/fr_sqr_proto.cuh, profiles/r1_imad_bench.jsonl).
+BJJ_HD void fr_sqr(Fr& r, const Fr& a) { fr_mul(r, a, a); }
 
 // ------------------------------------------------------------------------------------------------
 // conversions and helpers

@@ -6,6 +6,7 @@
 //   (bjj_cuda.cu: k_decompress_prepare / k_batch_inverse / k_decompress_finish for compressed input) ->
 //   k_verify_hash -> k_verify_split (EdDSA) -> k_verify_ec || k_verify_exact
 #include "kernels.h"
+#include "vmcurve.cuh"
 
 using namespace bjj;
 
@@ -39,19 +40,130 @@ __global__ void __launch_bounds__(BJJ_BLOCK, 4) k_verify_split(size_t n, const u
     BJJ_LANE_LOOP(n) lane_verify_split(s_base, s_stride, s_off, hm, plane, ok, i);
 }
 
-// Register budget left to the compiler (239 registers, 2 CTAs per SM): capping it at 168 for a third CTA
-// costs spills inside the Straus loop (measured 15.4 ms vs 11.7 ms per 2^18 lanes).  The register file is
-// partitioned per SMSP (16,384 registers each), so the exact-lane kernel cannot co-reside with this one
-// whatever the cap; it runs on a side stream and fills the tail instead.
-__global__ void __launch_bounds__(BJJ_BLOCK, 2) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+// Register budget: BJJ_VERIFY_EC_MINB resident CTAs per SM (2 -> up to 255 registers, 3 -> 168).  The recoded scalars
+// of the Straus pass live in shared memory (ScalarPark, 27 words per thread), not in registers.  The register file is
+// partitioned per SMSP (16,384 registers each), so the exact-lane kernel cannot co-reside with this one whatever
+// the cap; it runs on a side stream and fills the tail instead.
+#ifndef BJJ_VERIFY_EC_MINB
+#define BJJ_VERIFY_EC_MINB 2
+#endif
+__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_EC_MINB) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                          size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
                                                          int mode, unsigned long long* work) {
+    __shared__ uint32_t s_park[BJJ_PARK_WORDS * BJJ_BLOCK];
+    const ScalarPark park{s_park + threadIdx.x, BJJ_BLOCK};
     // two per-thread radix-16 tables (multiples of 8A and of R8), back to back
     const LaneTable tbl_a = thread_table(table);
     const LaneTable tbl_r = thread_table(table + (size_t)BJJ_TABLE_U128_PER_LANE * gridDim.x * blockDim.x);
     BJJ_CLAIM_LOOP(n, work)
-    if (i < n) lane_verify_ec(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode);
+    if (i < n) lane_verify_ec(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode, park);
+}
+
+// ---- the Straus pass on shared-memory slots (vm.cuh / vmcurve.cuh) --------------------------------------------
+// Same algorithm and tables as verify_fast (lanes.cuh); every field operation is a call into ~10 KB of resident
+// subroutines, a lane's working set is 11 slots (352 B) of shared memory, and BJJ_EC_VM_MINB CTAs share an SM.
+#ifndef BJJ_EC_VM
+#define BJJ_EC_VM 0
+#endif
+#ifndef BJJ_EC_VM_MINB
+#define BJJ_EC_VM_MINB 4
+#endif
+#define BJJ_EC_VM_SLOTS (BJJ_VM_REG_SLOTS + 2)
+
+__device__ __forceinline__ int vm_digit4(vm::Slot s, uint32_t top, int i) {      // signed radix-16 digit i in [0, 64]
+    const uint32_t w = vm::ld_word(s, (i >> 3) & 7);
+    return i == 64 ? (int)top : (int)((w >> ((i & 7) * 4)) & 15u) - 8;
+}
+__device__ __forceinline__ int vm_digit16(vm::Slot s, uint32_t top, int i) {     // signed radix-65536 digit i in [0, 16]
+    const uint32_t w = vm::ld_word(s, (i >> 1) & 7);
+    return i == 16 ? (int)top : (int)((w >> ((i & 1) * 16)) & 65535u) - 32768;
+}
+
+__device__ __forceinline__ void lane_verify_ec_vm(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
+                                                  const uint8_t* hm_in, size_t plane, uint8_t* ok, size_t i, const LaneTable& tbl_a,
+                                                  const LaneTable& tbl_r, const CombEntry* comb, int mode) {
+    using namespace vm;
+    const Regs s = regs_at(0);
+    const Slot su = slot(BJJ_VM_REG_SLOTS), sv = slot(BJJ_VM_REG_SLOTS + 1);
+    const Table ta = table_of(tbl_a), tr = table_of(tbl_r);
+    uint32_t tops, vneg;
+    int nwin;
+    {
+        uint32_t u[8], v[8];
+        load_u256(u, hm_in, plane + i);
+        load_u256(v, hm_in, 2 * plane + i);
+        vneg = v[7] >> 31;
+        v[7] &= 0x7FFFFFFFu;
+        Recode4 ru, rv;
+        recode4(ru, u);
+        recode4(rv, v);
+        nwin = recode4_windows(ru);
+        const int nv = recode4_windows(rv);
+        nwin = nwin > nv ? nwin : nv;
+        nwin = __reduce_max_sync(__activemask(), nwin);      // one trip count per warp (leading digits of a narrower lane are 0)
+        Fr t;
+        fr_set(t, ru.w);
+        st(su, t);
+        fr_set(t, rv.w);
+        st(sv, t);
+        tops = ru.top | (rv.top << 1);
+    }
+    // tables of -sign(v) * 8A (pk itself for Schnorr) and of -R8
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        load_mont(s.X, t == 0 ? ax : r8x, i);
+        load_mont(s.Y, t == 0 ? ay : r8y, i);
+        from_affine(s);
+        if (t == 0 && mode == BJJ_MODE_EDDSA) {
+#pragma unroll 1
+            for (int j = 0; j < 3; j++) dbl(s, j == 2);
+        }
+        if (t == 1 || !vneg) {       // negate: (-X, Y, Z, -T)
+            neg(s.X, s.X);
+            neg(s.T, s.T);
+        }
+        table_build(s, t == 0 ? ta : tr);
+    }
+    set_identity(s);
+#pragma unroll 1
+    for (int k = nwin - 1; k >= 0; k--) {
+        if (k != nwin - 1) {
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) dbl(s, j == 3);
+        }
+        add_digit(s, ta, vm_digit4(su, tops & 1u, k), true);
+        add_digit(s, tr, vm_digit4(sv, tops >> 1, k), k == 0);       // T only where the B8 additions follow
+    }
+    // + w * B8: 16 signed 16-bit digits and the recoding carry against the fixed-base table, no doubling
+    {
+        uint32_t w[8];
+        load_u256(w, hm_in, 3 * plane + i);
+        Recode16 rw;
+        recode16(rw, w);
+        Fr t;
+        fr_set(t, rw.w);
+        st(su, t);
+        tops = rw.top;
+    }
+#pragma unroll 1
+    for (int k = BJJ_COMB_WINDOWS - 1; k >= 0; k--) add_comb(s, comb, k, vm_digit16(su, tops, k), k != 0);
+    // acc == O = (0 : 1 : 1) ?   (Z != 0: complete formulas)
+    Fr x, y, z;
+    ld(x, s.X);
+    ld(y, s.Y);
+    ld(z, s.Z);
+    ok[i] = (fr_is_zero(x) && fr_eq(y, z)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(BJJ_VM_THREADS, BJJ_EC_VM_MINB) k_verify_ec_vm(size_t n, const uint8_t* r8x, const uint8_t* r8y,
+                                                                               const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
+                                                                               size_t plane, uint8_t* ok, U128* table,
+                                                                               const CombEntry* comb, int mode, unsigned long long* work) {
+    const LaneTable tbl_a = thread_table(table);
+    const LaneTable tbl_r = thread_table(table + (size_t)BJJ_TABLE_U128_PER_LANE * gridDim.x * blockDim.x);
+    BJJ_CLAIM_LOOP(n, work)
+    if (i < n && ok[i] == BJJ_OK_PENDING) lane_verify_ec_vm(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode);
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
@@ -79,7 +191,21 @@ static int occ(const void* k, int block) {
     return per_sm;
 }
 int verify_hash_blocks_per_sm() { return occ((const void*)k_verify_hash, BJJ_BLOCK); }
+#if BJJ_EC_VM
+static const size_t kEcVmSmem = vm::slot_bytes(BJJ_EC_VM_SLOTS);
+int verify_ec_blocks_per_sm() {
+    static int per_sm = [] {
+        cudaFuncSetAttribute((const void*)k_verify_ec_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEcVmSmem);
+        cudaFuncSetAttribute((const void*)k_verify_ec_vm, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, (const void*)k_verify_ec_vm, BJJ_VM_THREADS, kEcVmSmem) != cudaSuccess || v < 1) v = 1;
+        return v;
+    }();
+    return per_sm;
+}
+#else
 int verify_ec_blocks_per_sm() { return occ((const void*)k_verify_ec, BJJ_BLOCK); }
+#endif
 int verify_split_blocks_per_sm() { return occ((const void*)k_verify_split, BJJ_BLOCK); }
 
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
@@ -96,7 +222,11 @@ void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, si
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                const uint8_t* ay, const uint8_t* hm, size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
                int mode, unsigned long long* work) {
+#if BJJ_EC_VM
+    k_verify_ec_vm<<<grid, BJJ_VM_THREADS, kEcVmSmem, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode, work);
+#else
     k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode, work);
+#endif
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb,

@@ -857,8 +857,29 @@ BJJ_HD int recode4_digit_any(const Recode4& rc, int i) {   // i in [0, 64]
 // One Straus pass over the two per-lane points (radix-16 tables in global memory) runs as many windows as
 // the wider of u, |v| needs (32-33 after the split, 64-65 without); w * B8 is 17 additions from the
 // fixed-base table afterwards.
+// Recoded scalars parked outside the register file (shared memory on the device): word k of scalar s sits at
+// base[(9 * s + k) * stride]; word 8 is the recoding carry.  27 registers less for the Straus loop to carry.
+struct ScalarPark {
+    uint32_t* base;
+    int stride;
+};
+#define BJJ_PARK_WORDS 27
+BJJ_HD void park_store(const ScalarPark& pk, int s, const uint32_t* w, uint32_t top) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) pk.base[(9 * s + k) * pk.stride] = w[k];
+    pk.base[(9 * s + 8) * pk.stride] = top;
+}
+BJJ_HD int park_digit4(const ScalarPark& pk, int s, int i) {      // signed radix-16 digit i in [0, 64]
+    const uint32_t w = pk.base[(9 * s + (i >> 3)) * pk.stride];
+    return i == 64 ? (int)w : (int)((w >> ((i & 7) * 4)) & 15u) - 8;
+}
+BJJ_HD int park_digit16(const ScalarPark& pk, int s, int i) {     // signed radix-65536 digit i in [0, 16]
+    const uint32_t w = pk.base[(9 * s + (i >> 1)) * pk.stride];
+    return i == 16 ? (int)w : (int)((w >> ((i & 1) * 16)) & 65535u) - 32768;
+}
+
 BJJ_HD uint32_t verify_fast(const PointAff& r8, const PointAff& a, const VerifyScalars& sc, const LaneTable& tbl_a,
-                            const LaneTable& tbl_r, const CombEntry* comb, int mode) {
+                            const LaneTable& tbl_r, const CombEntry* comb, int mode, const ScalarPark& park) {
     PointExt acc;
     // tables of -sign(v) * 8A (pk itself for Schnorr, which multiplies pk by h) and of -R8.  Every loop below is
     // kept rolled: the kernel holds one inlined copy of the doubling and one of the addition (see curve.cuh).
@@ -878,14 +899,20 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const PointAff& a, const VerifyS
         if (t == 1) tb.base = tbl_r.base;
         table_build(tb, p);
     }
-    Recode4 ru, rv;
-    recode4(ru, sc.u);
-    recode4(rv, sc.v);
-    Recode16 rw;
-    recode16(rw, sc.w);
-    int nwin = recode4_windows(ru);
-    const int nv = recode4_windows(rv);
-    nwin = nwin > nv ? nwin : nv;
+    int nwin;
+    {
+        Recode4 ru, rv;
+        recode4(ru, sc.u);
+        recode4(rv, sc.v);
+        Recode16 rw;
+        recode16(rw, sc.w);
+        nwin = recode4_windows(ru);
+        const int nv = recode4_windows(rv);
+        nwin = nwin > nv ? nwin : nv;
+        park_store(park, 0, ru.w, ru.top);
+        park_store(park, 1, rv.w, rv.top);
+        park_store(park, 2, rw.w, rw.top);
+    }
     // Uniform trip counts matter beyond divergence: the warps of an SM share the instruction cache only while
     // they run the same stretch of the (large) loop body below, and a warp that finishes a lane one window early
     // is out of step for good -- with per-warp counts of 32-34 this kernel ran 2x slower (no_instruction stalls
@@ -911,16 +938,16 @@ BJJ_HD uint32_t verify_fast(const PointAff& r8, const PointAff& a, const VerifyS
             ext_dbl<true>(acc, acc);
         }
         Niels nn;
-        table_select(nn, tbl_a, recode4_digit_any(ru, i));
+        table_select(nn, tbl_a, park_digit4(park, 0, i));
         ext_add_niels<true>(acc, acc, nn);
-        table_select(nn, tbl_r, recode4_digit_any(rv, i));
+        table_select(nn, tbl_r, park_digit4(park, 1, i));
         ext_add_niels_rt(acc, acc, nn, false, i == 0);      // T only where the B8 additions follow
     }
     // + w * B8: 16 signed 16-bit digits and the recoding carry against the fixed-base table, no doubling
 #pragma unroll 1
     for (int k = BJJ_COMB_WINDOWS - 1; k >= 0; k--) {
         NielsAff nb;
-        comb_select(nb, comb, k, k == BJJ_COMB_WINDOWS - 1 ? (int)rw.top : recode16_digit(rw, k));
+        comb_select(nb, comb, k, park_digit16(park, 2, k));
         Niels nn;
         nn.ypx = nb.ypx;
         nn.ymx = nb.ymx;
@@ -1095,7 +1122,7 @@ BJJ_HD void lane_verify_split(const uint8_t* s_base, size_t s_stride, size_t s_o
 
 BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
                            const uint8_t* hm_in, size_t plane, uint8_t* ok, size_t i, const LaneTable& tbl_a,
-                           const LaneTable& tbl_r, const CombEntry* comb, int mode) {
+                           const LaneTable& tbl_r, const CombEntry* comb, int mode, const ScalarPark& park) {
     if (ok[i] != BJJ_OK_PENDING) return;
     uint32_t flags = 0;
     PointAff r8, a;
@@ -1109,7 +1136,7 @@ BJJ_HD void lane_verify_ec(const uint8_t* r8x, const uint8_t* r8y, const uint8_t
     load_fr(r8.y, r8y, i, flags);
     load_fr(a.x, ax, i, flags);
     load_fr(a.y, ay, i, flags);
-    ok[i] = (uint8_t)verify_fast(r8, a, sc, tbl_a, tbl_r, comb, mode);
+    ok[i] = (uint8_t)verify_fast(r8, a, sc, tbl_a, tbl_r, comb, mode, park);
 }
 
 template <bool A_OFF>

@@ -1,0 +1,125 @@
+// Field arithmetic on operands that live in SHARED memory, as out-of-line subroutines.
+//
+// Why: one inlined Montgomery multiplication is ~3 KB of SASS.  A curve formula inlined into a kernel is
+// 25-30 KB, a Straus window (4 doublings + 2 additions) 150 KB -- against a 32 KB L1.5 instruction cache and
+// ~6 KB L0 per SM sub-partition (guides/B300_MICROARCH.md "I-cache").  Once the warps of an SM drift apart, a
+// straight-line body of that size is re-fetched from L2 by every warp and the kernel stalls on instruction
+// supply (round 1: k_verify_ec, `no_instruction` 1.2 stalls per issue, multiplier pipe 66-78 % busy;
+// tools/microbench/fr_layouts.cu `footprint` lines measure the cliff directly).  Calling ONE copy of the
+// multiplier with register operands was no way out either: a by-value call moves ~45 registers per call.
+//
+// Here a field element is a SLOT of shared memory (2 x 16 B per thread, lane-interleaved so that a warp's
+// LDS.128/STS.128 is conflict-free) and every operation is `op(dst_slot, a_slot, b_slot)`: a call passes three
+// 32-bit slot indices, the callee loads its operands with LDS.128, works in registers and stores the result.  The
+// whole arithmetic of a kernel is then ~8 KB of code (mul, mul2, add, sub) that stays in the instruction caches,
+// the caller keeps almost nothing in registers (more resident warps), and the shared-memory traffic is
+// 96 B per thread per multiplication against 544 multiplier-pipe cycles per warp: ~18 % of the LDS/STS bandwidth.
+//
+// Reference items built on this: Point::mul_scalar (src/lib.rs:149-164) and verify (src/lib.rs:395-412) through
+// vmcurve.cuh.  Device-only (the host test harness checks the SAME formulas through curve.cuh; the GPU parity
+// tests check these kernels bit for bit against the oracle).
+#pragma once
+#include "fr.cuh"
+
+#if defined(__CUDACC__) && !defined(BJJ_HOST_EMU)
+
+namespace bjj {
+namespace vm {
+
+#define BJJ_VM_THREADS 128          // CTA size of every kernel that uses these primitives
+
+extern __shared__ uint4 g_slots[];  // [slot][half][thread]
+
+typedef uint32_t Slot;              // uint4 index of (slot, half 0) for THIS thread
+
+__device__ __forceinline__ Slot slot(int s) { return (uint32_t)s * (2 * BJJ_VM_THREADS) + threadIdx.x; }
+__host__ __device__ constexpr size_t slot_bytes(int nslots) { return (size_t)nslots * 2 * BJJ_VM_THREADS * sizeof(uint4); }
+
+__device__ __forceinline__ void ld(Fr& r, Slot s) {
+    const uint4 a = g_slots[s], b = g_slots[s + BJJ_VM_THREADS];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void st(Slot s, const Fr& r) {
+    g_slots[s] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    g_slots[s + BJJ_VM_THREADS] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// one 32-bit word of a slot (scalars parked in slots: recoded digits)
+__device__ __forceinline__ uint32_t ld_word(Slot s, int k) {
+    return reinterpret_cast<const uint32_t*>(g_slots)[(size_t)(s + (k >> 2) * BJJ_VM_THREADS) * 4 + (k & 3)];
+}
+
+// global operand: two 16-byte halves `hstride` uint4 apart (1 for a contiguous 32-byte element)
+__device__ __forceinline__ void ldg(Fr& r, const uint4* p, size_t hstride) {
+    const uint4 a = __ldg(p), b = __ldg(p + hstride);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void stg(uint4* p, size_t hstride, const Fr& r) {
+    p[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    p[hstride] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// ---- the out-of-line operations --------------------------------------------------------------------
+// d = a * b
+static __device__ __noinline__ void mul(Slot d, Slot a, Slot b) {
+    Fr x, y, r;
+    ld(x, a);
+    ld(y, b);
+    fr_mul_inline(r, x, y);
+    st(d, r);
+}
+// two independent multiplications in one call: d0 = a0 * b0, d1 = a1 * b1 (twice the carry chains in flight)
+static __device__ __noinline__ void mul2(Slot d0, Slot a0, Slot b0, Slot d1, Slot a1, Slot b1) {
+    Fr x0, y0, x1, y1, r0, r1;
+    ld(x0, a0);
+    ld(y0, b0);
+    ld(x1, a1);
+    ld(y1, b1);
+    fr_mul_inline(r0, x0, y0);
+    fr_mul_inline(r1, x1, y1);
+    st(d0, r0);
+    st(d1, r1);
+}
+// the same with the second factors read from global memory (window-table / comb entries)
+static __device__ __noinline__ void mul2_g(Slot d0, Slot a0, const uint4* g0, Slot d1, Slot a1, const uint4* g1, size_t hstride) {
+    Fr x0, y0, x1, y1, r0, r1;
+    ldg(y0, g0, hstride);
+    ldg(y1, g1, hstride);
+    ld(x0, a0);
+    ld(x1, a1);
+    fr_mul_inline(r0, x0, y0);
+    fr_mul_inline(r1, x1, y1);
+    st(d0, r0);
+    st(d1, r1);
+}
+// d = a + b, d = a - b (lazy domain [0, 2Q))
+static __device__ __noinline__ void add(Slot d, Slot a, Slot b) {
+    Fr x, y, r;
+    ld(x, a);
+    ld(y, b);
+    fr_add(r, x, y);
+    st(d, r);
+}
+static __device__ __noinline__ void sub(Slot d, Slot a, Slot b) {
+    Fr x, y, r;
+    ld(x, a);
+    ld(y, b);
+    fr_sub(r, x, y);
+    st(d, r);
+}
+// both at once: s = a + b, d = a - b (the (Y+X, Y-X) and (H, G) pairs of the curve formulas)
+static __device__ __noinline__ void addsub(Slot s, Slot d, Slot a, Slot b) {
+    Fr x, y, r;
+    ld(x, a);
+    ld(y, b);
+    fr_add(r, x, y);
+    st(s, r);
+    fr_sub(r, x, y);
+    st(d, r);
+}
+
+}  // namespace vm
+}  // namespace bjj
+
+#endif

@@ -12,9 +12,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "fr.cuh"
+#include "../../csrc/fr.cuh"
 #include "fr29_proto.cuh"
 #include "fr52_proto.cuh"
+#include "fr_sqr_proto.cuh"
 
 using namespace bjj;
 
@@ -75,7 +76,7 @@ __global__ void k_fr_mul(uint32_t* out, int iters, uint32_t seed) {
 #pragma unroll
         for (int k = 0; k < ILP; k++) {
             if (SQR)
-                fr_sqr(x[k], x[k]);
+                fr_sqr_dedicated(x[k], x[k]);
             else
                 fr_mul(x[k], x[k], y[k]);
         }

@@ -62,6 +62,10 @@ static void batch_affine(const ProjScratch& s, uint8_t* rx, uint8_t* ry, size_t 
     for (size_t t = 0; t < T; t++) batch_affine_strided(s, rx, ry, n, t, T);
 }
 
+static ScalarPark host_park() {
+    static uint32_t words[BJJ_PARK_WORDS];
+    return ScalarPark{words, 1};
+}
 static LaneTable lane_table(int which = 0) {
     LaneTable t;
     t.base = g_table.data() + (size_t)which * BJJ_TABLE_U128_PER_LANE;
@@ -193,7 +197,7 @@ uint32_t emu_verify(size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint
         lane_verify_hash(r8x, r8y, ax, ay, msg, s, 1, 0, nullptr, hm.data(), n, ok, i, true, qa, qr, flags, BJJ_MODE_EDDSA, g_split, nullptr);
     if (g_split)
         for (size_t i = 0; i < n; i++) lane_verify_split(s, 1, 0, hm.data(), n, ok, i);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, ax, ay, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_EDDSA);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(r8x, r8y, ax, ay, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_EDDSA, host_park());
     for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list[j], g_comb, BJJ_MODE_EDDSA);
     for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm.data(), ok, g_list2[j], g_comb, BJJ_MODE_EDDSA);
     return flags;
@@ -207,7 +211,7 @@ uint32_t emu_verify_schnorr(size_t n, const uint8_t* pkx, const uint8_t* pky, co
     std::vector<uint8_t> hm(4 * 32 * (n + 1));
     for (size_t i = 0; i < n; i++)
         lane_verify_hash(rx, ry, pkx, pky, msg, s, 1, 0, nullptr, hm.data(), n, ok, i, true, qa, qr, flags, BJJ_MODE_SCHNORR, g_split, status);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(rx, ry, pkx, pky, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_SCHNORR);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(rx, ry, pkx, pky, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_SCHNORR, host_park());
     for (uint32_t j = 0; j < g_count; j++) lane_verify_exact<true>(rx, ry, s, pkx, pky, hm.data(), ok, g_list[j], g_comb, BJJ_MODE_SCHNORR);
     for (uint32_t j = 0; j < g_count2; j++) lane_verify_exact<false>(rx, ry, s, pkx, pky, hm.data(), ok, g_list2[j], g_comb, BJJ_MODE_SCHNORR);
     return flags;
@@ -230,7 +234,7 @@ void emu_verify_compressed(size_t n, const uint8_t* sig64, const uint8_t* pk32, 
         lane_verify_hash(dx, dy, ax, ay, msg, sig64, 2, 1, status, hm.data(), n, ok, i, false, q, q, flags, BJJ_MODE_EDDSA, g_split, nullptr);
     if (g_split)
         for (size_t i = 0; i < n; i++) lane_verify_split(sig64, 2, 1, hm.data(), n, ok, i);
-    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, ax, ay, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_EDDSA);
+    for (size_t i = 0; i < n; i++) lane_verify_ec(dx, dy, ax, ay, hm.data(), n, ok, i, lane_table(0), lane_table(1), g_comb, BJJ_MODE_EDDSA, host_park());
 }
 
 // verify's half-size scalar split (split.cuh), for the invariant tests: u = v * h (mod l), v odd
