@@ -449,3 +449,96 @@ def verify_batch_multi(mg, r8x, r8y, s, ax, ay, msg):
         ok[lo:hi] = eng.verify_batch(*[v[lo:hi] for v in ins])
     mg.run_sharded(len(ok), work)
     return ok
+
+
+class MultiEngine:
+    """bjj_multi (include/bjj_cuda.h): ONE caller, ONE host batch, every device of the box -- config 4 as written.
+
+    The library owns one context and one persistent host thread per device; a call cuts the arrays into
+    contiguous shards and returns when all are done.  No NCCL: lanes never exchange anything.  `out=` lets a
+    caller supply pinned result buffers (bjj_host_alloc); inputs may be pageable or pinned numpy arrays."""
+
+    def __init__(self, devices=None, host_register=False):
+        self.lib = _lib.load()
+        if self.lib.bjj_device_count() < 1:
+            raise RuntimeError("babyjubjub-rs_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        handle = ctypes.c_void_p()
+        if devices is None:
+            rc = self.lib.bjj_multi_init(0, None, ctypes.byref(handle))
+        else:
+            arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.bjj_multi_init(len(devices), arr, ctypes.byref(handle))
+        if rc != 0:
+            raise BjjError(rc, "bjj_multi_init", self.lib.bjj_error_string(rc).decode())
+        self.handle = handle
+        self.lib.bjj_multi_set_host_register(self.handle, 1 if host_register else 0)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bjj_multi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def devices(self):
+        return int(self.lib.bjj_multi_devices(self.handle))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.bjj_multi_kernel_launches(self.handle))
+
+    def set_host_register(self, on):
+        self.lib.bjj_multi_set_host_register(self.handle, 1 if on else 0)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise BjjError(rc, what, self.lib.bjj_error_string(rc).decode())
+
+    def verify_batch(self, r8x, r8y, s, ax, ay, msg, out=None):
+        ins = [_as_u8(v, 32) for v in (r8x, r8y, s, ax, ay, msg)]
+        ok = np.empty(len(ins[0]), dtype=np.uint8) if out is None else out
+        self._check(self.lib.bjj_multi_verify_batch(self.handle, len(ins[0]), *[_ptr(v) for v in ins], _ptr(ok)),
+                    "bjj_multi_verify_batch")
+        return ok
+
+    def verify_compressed_batch(self, sig64, pk32, msg, out=None):
+        sig64, pk32, msg = _as_u8(sig64, 64), _as_u8(pk32, 32), _as_u8(msg, 32)
+        n = len(sig64)
+        ok, st = (np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)) if out is None else out
+        self._check(self.lib.bjj_multi_verify_compressed_batch(self.handle, n, _ptr(sig64), _ptr(pk32), _ptr(msg), _ptr(ok),
+                                                               _ptr(st)), "bjj_multi_verify_compressed_batch")
+        return ok, st
+
+    def mul_scalar_batch(self, px, py, scalars, out=None):
+        px, py, k = _as_u8(px, 32), _as_u8(py, 32), _as_u8(scalars, 32)
+        rx, ry = (np.empty_like(px), np.empty_like(px)) if out is None else out
+        self._check(self.lib.bjj_multi_mul_scalar_batch(self.handle, len(px), _ptr(px), _ptr(py), _ptr(k), _ptr(rx), _ptr(ry)),
+                    "bjj_multi_mul_scalar_batch")
+        return rx, ry
+
+    def public_batch(self, keys, out=None):
+        keys = _as_u8(keys, 32)
+        rx, ry = (np.empty_like(keys), np.empty_like(keys)) if out is None else out
+        self._check(self.lib.bjj_multi_public_batch(self.handle, len(keys), _ptr(keys), _ptr(rx), _ptr(ry)),
+                    "bjj_multi_public_batch")
+        return rx, ry
+
+    def fixed_base_batch(self, scalars, out=None):
+        k = _as_u8(scalars, 32)
+        rx, ry = (np.empty_like(k), np.empty_like(k)) if out is None else out
+        self._check(self.lib.bjj_multi_fixed_base_batch(self.handle, len(k), _ptr(k), _ptr(rx), _ptr(ry)),
+                    "bjj_multi_fixed_base_batch")
+        return rx, ry
+
+    def decompress_batch(self, comp, out=None):
+        comp = _as_u8(comp, 32)
+        n = len(comp)
+        rx, ry, st = (np.empty_like(comp), np.empty_like(comp), np.empty(n, dtype=np.uint8)) if out is None else out
+        self._check(self.lib.bjj_multi_decompress_batch(self.handle, n, _ptr(comp), _ptr(rx), _ptr(ry), _ptr(st)),
+                    "bjj_multi_decompress_batch")
+        return rx, ry, st

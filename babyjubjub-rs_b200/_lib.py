@@ -49,6 +49,23 @@ for _name in [k for k in SIGNATURES if k.endswith("_batch")]:
     _res, _args = SIGNATURES[_name]
     SIGNATURES[_name + "_dev"] = (_res, list(_args) + [ctypes.c_void_p])
 
+# multi-device layer (one caller, one host batch, N devices); host pointers only
+_multi = ctypes.c_void_p
+SIGNATURES.update({
+    "bjj_multi_init": (_int, [_int, ctypes.POINTER(_int), ctypes.POINTER(_multi)]),
+    "bjj_multi_destroy": (None, [_multi]),
+    "bjj_multi_devices": (_int, [_multi]),
+    "bjj_multi_ctx": (_ctx, [_multi, _int]),
+    "bjj_multi_set_host_register": (None, [_multi, _int]),
+    "bjj_multi_kernel_launches": (ctypes.c_ulonglong, [_multi]),
+    "bjj_multi_verify_batch": (_int, [_multi, _sz] + [_u8p] * 7),
+    "bjj_multi_verify_compressed_batch": (_int, [_multi, _sz] + [_u8p] * 5),
+    "bjj_multi_mul_scalar_batch": (_int, [_multi, _sz] + [_u8p] * 5),
+    "bjj_multi_public_batch": (_int, [_multi, _sz] + [_u8p] * 3),
+    "bjj_multi_fixed_base_batch": (_int, [_multi, _sz] + [_u8p] * 3),
+    "bjj_multi_decompress_batch": (_int, [_multi, _sz] + [_u8p] * 4),
+})
+
 _lib = None
 
 

@@ -4,7 +4,9 @@
 // One verification is a short pipeline of kernels, so that no kernel carries another phase's registers
 // or instruction footprint:
 //   (bjj_cuda.cu: k_decompress_prepare / k_batch_inverse / k_decompress_finish for compressed input) ->
-//   k_verify_hash -> k_verify_split (EdDSA) -> k_verify_ec || k_verify_exact
+//   k_verify_hash -> k_verify_split (EdDSA) -> k_verify_ec_vm || k_verify_exact
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "vmcurve.cuh"
 
@@ -40,34 +42,15 @@ __global__ void __launch_bounds__(BJJ_BLOCK, 4) k_verify_split(size_t n, const u
     BJJ_LANE_LOOP(n) lane_verify_split(s_base, s_stride, s_off, hm, plane, ok, i);
 }
 
-// Register budget: BJJ_VERIFY_EC_MINB resident CTAs per SM (2 -> up to 255 registers, 3 -> 168).  The recoded scalars
-// of the Straus pass live in shared memory (ScalarPark, 27 words per thread), not in registers.  The register file is
-// partitioned per SMSP (16,384 registers each), so the exact-lane kernel cannot co-reside with this one whatever
-// the cap; it runs on a side stream and fills the tail instead.
-#ifndef BJJ_VERIFY_EC_MINB
-#define BJJ_VERIFY_EC_MINB 2
-#endif
-__global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_EC_MINB) k_verify_ec(size_t n, const uint8_t* r8x, const uint8_t* r8y,
-                                                         const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
-                                                         size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
-                                                         int mode, unsigned long long* work) {
-    __shared__ uint32_t s_park[BJJ_PARK_WORDS * BJJ_BLOCK];
-    const ScalarPark park{s_park + threadIdx.x, BJJ_BLOCK};
-    // two per-thread radix-16 tables (multiples of 8A and of R8), back to back
-    const LaneTable tbl_a = thread_table(table);
-    const LaneTable tbl_r = thread_table(table + (size_t)BJJ_TABLE_U128_PER_LANE * gridDim.x * blockDim.x);
-    BJJ_CLAIM_LOOP(n, work)
-    if (i < n) lane_verify_ec(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode, park);
-}
-
 // ---- the Straus pass on shared-memory slots (vm.cuh / vmcurve.cuh) --------------------------------------------
-// Same algorithm and tables as verify_fast (lanes.cuh); every field operation is a call into ~10 KB of resident
-// subroutines, a lane's working set is 11 slots (352 B) of shared memory, and BJJ_EC_VM_MINB CTAs share an SM.
-#ifndef BJJ_EC_VM
-#define BJJ_EC_VM 0
-#endif
+// The algorithm and tables of verify_fast (lanes.cuh, the host-checkable statement of the same pass); every field
+// operation is a call into ~20 KB of resident subroutines, a lane's working set is 11 slots (352 B) of shared
+// memory, and BJJ_EC_VM_MINB CTAs (5 x 4 warps, 96 registers) share an SM.  Measured on one GPU against the inlined
+// kernel of round 1 (228 registers, 2 CTAs per SM, 150 KB window body): 60.4 ms against 66.2 ms per 2^21 lanes,
+// multiplier pipe 86 % against 66-78 % busy, `no_instruction` 0.17 against 1.2 stalls per issue
+// (profiles/r2_ab_verify_ec.txt, profiles/r2_ncu_verify_ec_summary.txt).
 #ifndef BJJ_EC_VM_MINB
-#define BJJ_EC_VM_MINB 4
+#define BJJ_EC_VM_MINB 5
 #endif
 #define BJJ_EC_VM_SLOTS (BJJ_VM_REG_SLOTS + 2)
 
@@ -81,12 +64,11 @@ __device__ __forceinline__ int vm_digit16(vm::Slot s, uint32_t top, int i) {    
 }
 
 __device__ __forceinline__ void lane_verify_ec_vm(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax, const uint8_t* ay,
-                                                  const uint8_t* hm_in, size_t plane, uint8_t* ok, size_t i, const LaneTable& tbl_a,
-                                                  const LaneTable& tbl_r, const CombEntry* comb, int mode) {
+                                                  const uint8_t* hm_in, size_t plane, uint8_t* ok, size_t i, const vm::Table& ta,
+                                                  const vm::Table& tr, const CombEntry* comb, int mode) {
     using namespace vm;
     const Regs s = regs_at(0);
     const Slot su = slot(BJJ_VM_REG_SLOTS), sv = slot(BJJ_VM_REG_SLOTS + 1);
-    const Table ta = table_of(tbl_a), tr = table_of(tbl_r);
     uint32_t tops, vneg;
     int nwin;
     {
@@ -160,10 +142,11 @@ __global__ void __launch_bounds__(BJJ_VM_THREADS, BJJ_EC_VM_MINB) k_verify_ec_vm
                                                                                const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                                                size_t plane, uint8_t* ok, U128* table,
                                                                                const CombEntry* comb, int mode, unsigned long long* work) {
-    const LaneTable tbl_a = thread_table(table);
-    const LaneTable tbl_r = thread_table(table + (size_t)BJJ_TABLE_U128_PER_LANE * gridDim.x * blockDim.x);
+    // two per-thread radix-16 tables (multiples of 8A and of R8), each thread's 2 x 9 entries contiguous
+    const size_t tslot = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const vm::Table ta = vm::table_of(table, tslot), tr = vm::table_of(table, tslot + 1);
     BJJ_CLAIM_LOOP(n, work)
-    if (i < n && ok[i] == BJJ_OK_PENDING) lane_verify_ec_vm(r8x, r8y, ax, ay, hm, plane, ok, i, tbl_a, tbl_r, comb, mode);
+    if (i < n && ok[i] == BJJ_OK_PENDING) lane_verify_ec_vm(r8x, r8y, ax, ay, hm, plane, ok, i, ta, tr, comb, mode);
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
@@ -191,7 +174,6 @@ static int occ(const void* k, int block) {
     return per_sm;
 }
 int verify_hash_blocks_per_sm() { return occ((const void*)k_verify_hash, BJJ_BLOCK); }
-#if BJJ_EC_VM
 static const size_t kEcVmSmem = vm::slot_bytes(BJJ_EC_VM_SLOTS);
 int verify_ec_blocks_per_sm() {
     static int per_sm = [] {
@@ -199,13 +181,16 @@ int verify_ec_blocks_per_sm() {
         cudaFuncSetAttribute((const void*)k_verify_ec_vm, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, (const void*)k_verify_ec_vm, BJJ_VM_THREADS, kEcVmSmem) != cudaSuccess || v < 1) v = 1;
+        // BJJ_EC_CTAS_PER_SM=n (experiments): fewer resident CTAs than fit, e.g. to leave registers for the exact-lane kernel
+        if (const char* e = getenv("BJJ_EC_CTAS_PER_SM")) {
+            const int cap = atoi(e);
+            if (cap >= 1 && cap < v) v = cap;
+        }
         return v;
     }();
     return per_sm;
 }
-#else
-int verify_ec_blocks_per_sm() { return occ((const void*)k_verify_ec, BJJ_BLOCK); }
-#endif
+
 int verify_split_blocks_per_sm() { return occ((const void*)k_verify_split, BJJ_BLOCK); }
 
 void verify_hash(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
@@ -222,11 +207,7 @@ void verify_split(int grid, cudaStream_t st, size_t n, const uint8_t* s_base, si
 void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* ax,
                const uint8_t* ay, const uint8_t* hm, size_t plane, uint8_t* ok, U128* table, const CombEntry* comb,
                int mode, unsigned long long* work) {
-#if BJJ_EC_VM
     k_verify_ec_vm<<<grid, BJJ_VM_THREADS, kEcVmSmem, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode, work);
-#else
-    k_verify_ec<<<grid, BJJ_BLOCK, 0, st>>>(n, r8x, r8y, ax, ay, hm, plane, ok, table, comb, mode, work);
-#endif
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb,

@@ -141,16 +141,19 @@ __device__ __forceinline__ void store_niels(const Regs& s, uint4* e, size_t cstr
     put(e + 3 * cstride, hstride, s.t3);
 }
 
-// per-thread window table in global memory, the layout of lanes.cuh::LaneTable (entry j = j * P, j = 0..8)
+// Per-thread window table in global memory: entry j = j * P (j = 0..8) is 128 contiguous bytes (y+x | y-x | 2d'T | 2Z)
+// and a thread's nine entries are contiguous.  The lanes of a warp pick different entries, so what matters for L2
+// and HBM is that every 32-byte sector fetched is used: with the entry in one 128-byte line it is (the interleaved
+// layout of lanes.cuh::LaneTable, which coalesces only when all lanes pick the same entry, fetched twice the bytes).
 struct Table {
-    uint4* base;      // entry 0, coordinate 0, half 0 of THIS thread
-    size_t stride;    // resident threads (uint4 units between consecutive (coordinate, half) planes)
-    __device__ __forceinline__ uint4* entry(int j) const { return base + (size_t)j * 8 * stride; }
+    uint4* base;      // entry 0 of THIS thread
+    __device__ __forceinline__ uint4* entry(int j) const { return base + (size_t)j * 8; }
 };
-__device__ __forceinline__ Table table_of(const LaneTable& t) {
+#define BJJ_VM_TABLE_CSTRIDE 2      // uint4 between coordinates of an entry
+#define BJJ_VM_TABLE_HSTRIDE 1      // uint4 between the halves of a coordinate
+__device__ __forceinline__ Table table_of(U128* pool, size_t thread_slot) {
     Table r;
-    r.base = reinterpret_cast<uint4*>(t.base) + t.slot;
-    r.stride = t.stride;
+    r.base = reinterpret_cast<uint4*>(pool) + thread_slot * BJJ_TABLE_U128_PER_LANE;
     return r;
 }
 
@@ -160,22 +163,22 @@ __device__ __forceinline__ void table_build(const Regs& s, const Table& tb) {
     set01(s.t0, 1);
     set01(s.t2, 0);
     add(s.t3, s.t0, s.t0);
-    put(tb.entry(0), tb.stride, s.t0);
-    put(tb.entry(0) + 2 * tb.stride, tb.stride, s.t0);
-    put(tb.entry(0) + 4 * tb.stride, tb.stride, s.t2);
-    put(tb.entry(0) + 6 * tb.stride, tb.stride, s.t3);
-    store_niels(s, tb.entry(1), 2 * tb.stride, tb.stride);
+    put(tb.entry(0), BJJ_VM_TABLE_HSTRIDE, s.t0);
+    put(tb.entry(0) + BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE, s.t0);
+    put(tb.entry(0) + 2 * BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE, s.t2);
+    put(tb.entry(0) + 3 * BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE, s.t3);
+    store_niels(s, tb.entry(1), BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE);
 #pragma unroll 1
     for (int j = 2; j <= 8; j++) {
-        add_entry(s, tb.entry(1), 2 * tb.stride, tb.stride, false, false, true);
-        store_niels(s, tb.entry(j), 2 * tb.stride, tb.stride);
+        add_entry(s, tb.entry(1), BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE, false, false, true);
+        store_niels(s, tb.entry(j), BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE);
     }
 }
 
 // acc += d * P for a signed digit d in [-8, 8]
 __device__ __forceinline__ void add_digit(const Regs& s, const Table& tb, int d, bool want_t) {
     const int ad = d < 0 ? -d : d;
-    add_entry(s, tb.entry(ad), 2 * tb.stride, tb.stride, d < 0, false, want_t);
+    add_entry(s, tb.entry(ad), BJJ_VM_TABLE_CSTRIDE, BJJ_VM_TABLE_HSTRIDE, d < 0, false, want_t);
 }
 // acc += d * 65536^w * B8 from the fixed-base table (lanes.cuh::comb_select)
 __device__ __forceinline__ void add_comb(const Regs& s, const CombEntry* comb, int w, int d, bool want_t) {

@@ -29,7 +29,7 @@ OUT = os.path.join(ROOT, "ab_variants")
 LIB = os.path.join(PKG, "libbjj_cuda.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "20091", "-Xcompiler", "-fPIC"]
-OTHER_UNITS = ["bjj_cuda", "k_mulscalar", "k_sign", "k_poseidon"]
+OTHER_UNITS = ["bjj_cuda", "bjj_multi", "k_mulscalar", "k_sign", "k_poseidon"]
 
 
 def build(specs):

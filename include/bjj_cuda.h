@@ -173,6 +173,31 @@ int bjj_verify_compressed_batch(bjj_ctx* ctx, size_t n, const uint8_t* sig64, co
 int bjj_verify_compressed_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
                                     const uint8_t* msg32, uint8_t* ok, uint8_t* status, void* stream);
 
+/* ---- multi-device: ONE caller, ONE host batch, N devices of one box -------------------------------
+ * BASELINE.json config 4 as written (2^24 signatures across 8 B200 from one caller).  The reference has no
+ * counterpart (it is single-threaded: src/lib.rs:395-412 verifies one signature); a rayon par_iter over a
+ * batch is what this replaces.  A bjj_multi owns one bjj_ctx and one persistent host thread per device; a call
+ * cuts the arrays into contiguous shards (lane i of shard d is lane n*d/N + i of the batch), runs the ordinary
+ * host-pointer entry point on every shard concurrently and returns when all are done.  No NCCL, no peer access:
+ * nothing is exchanged between lanes.  Arrays may be pageable or pinned (bjj_host_alloc); with
+ * bjj_multi_set_host_register(m, 1) pageable arrays are page-locked for the duration of each call. */
+typedef struct bjj_multi bjj_multi;
+int bjj_multi_init(int n_devices, const int* devices, bjj_multi** out);   /* n_devices <= 0: all; devices NULL: 0..n-1 */
+void bjj_multi_destroy(bjj_multi* m);
+int bjj_multi_devices(bjj_multi* m);
+bjj_ctx* bjj_multi_ctx(bjj_multi* m, int i);                              /* the context of device slot i */
+void bjj_multi_set_host_register(bjj_multi* m, int on);
+unsigned long long bjj_multi_kernel_launches(bjj_multi* m);
+int bjj_multi_verify_batch(bjj_multi* m, size_t n, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s32,
+                           const uint8_t* ax, const uint8_t* ay, const uint8_t* msg32, uint8_t* ok);
+int bjj_multi_verify_compressed_batch(bjj_multi* m, size_t n, const uint8_t* sig64, const uint8_t* pk32,
+                                      const uint8_t* msg32, uint8_t* ok, uint8_t* status);
+int bjj_multi_mul_scalar_batch(bjj_multi* m, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar32,
+                               uint8_t* rx, uint8_t* ry);
+int bjj_multi_public_batch(bjj_multi* m, size_t n, const uint8_t* key32, uint8_t* rx, uint8_t* ry);
+int bjj_multi_fixed_base_batch(bjj_multi* m, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry);
+int bjj_multi_decompress_batch(bjj_multi* m, size_t n, const uint8_t* in32, uint8_t* rx, uint8_t* ry, uint8_t* status);
+
 #ifdef __cplusplus
 }
 #endif

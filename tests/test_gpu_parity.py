@@ -134,14 +134,54 @@ def test_large_batch_properties(gpu, oracle_c):
 
 
 def test_multi_device_sharding(gpu, oracle_c):
-    """verify_batch sharded over every visible device (one on the test box) equals the oracle"""
+    """verify_batch sharded over every visible device equals the oracle; on a multi-GPU box every device takes part"""
     import random
     from common import cases_to_arrays, signature_cases
     bjj = gpu.bjj
+    ndev = bjj._lib.load().bjj_device_count()
     mg = bjj.multi_gpu()
+    assert len(mg.engines) == ndev
+    if ndev > 1:
+        assert len(mg.engines) > 1
     arrs = cases_to_arrays(signature_cases(random.Random(21), 5))
     ok = bjj.verify_batch_multi(mg, *arrs)
     assert np.array_equal(ok, oracle_c.verify(*arrs))
+
+
+def test_multi_engine_single_caller(gpu, oracle_c):
+    """bjj_multi_*: ONE host batch cut into contiguous shards over every device by the library's own threads
+    (config 4 as written).  Results must equal the single-device calls and the oracle, with pageable inputs, with
+    page-locking on, and with lane counts that do not divide by the device count."""
+    import random
+    from common import cases_to_arrays, signature_cases
+    bjj = gpu.bjj
+    ndev = bjj._lib.load().bjj_device_count()
+    me = bjj.MultiEngine()
+    assert me.devices == ndev
+    arrs = cases_to_arrays(signature_cases(random.Random(33), 7))
+    exp = oracle_c.verify(*arrs)
+    assert np.array_equal(me.verify_batch(*arrs), exp)
+    me.set_host_register(True)
+    assert np.array_equal(me.verify_batch(*arrs), exp)
+    me.set_host_register(False)
+    # ragged sizes: fewer lanes than devices, and a prime lane count
+    for n in (1, 3, 1009):
+        k = pack([(i * 0x9E3779B97F4A7C15 + 777) % (1 << 253) for i in range(n)])
+        gx, gy = me.fixed_base_batch(k)
+        ex, ey = oracle_c.fixed_base(k)
+        assert np.array_equal(gx, ex) and np.array_equal(gy, ey)
+        px, py = me.public_batch(k)
+        sx, sy = gpu.eng.public_batch(k)
+        assert np.array_equal(px, sx) and np.array_equal(py, sy)
+        mx, my = me.mul_scalar_batch(gx, gy, k)
+        qx, qy = oracle_c.mul_scalar(gx, gy, k)
+        assert np.array_equal(mx, qx) and np.array_equal(my, qy)
+        comp = gpu.eng.compress_batch(gx, gy)
+        dx, dy, st = me.decompress_batch(comp)
+        assert not st.any() and np.array_equal(dx, gx) and np.array_equal(dy, gy)
+    launches = me.kernel_launches
+    assert launches > 0
+    me.close()
 
 
 def test_device_pointer_flavour_across_subbatches(gpu, oracle_c):
