@@ -150,6 +150,16 @@ class Engine:
                     "bjj_mul_scalar_batch")
         return tuple(outs)
 
+    def mul_scalar_wide_batch(self, px, py, scalars, words):
+        """scalars: uint8 array (n, 4 * words), little-endian; words a multiple of 8 in [8, 64] (src/lib.rs:149-164
+        takes a BigInt of any size)"""
+        px, py = _as_u8(px, 32), _as_u8(py, 32)
+        k = _as_u8(scalars, 4 * int(words))
+        rx, ry = np.empty_like(px), np.empty_like(px)
+        self._check(self.lib.bjj_mul_scalar_wide_batch(self.ctx, len(px), _ptr(px), _ptr(py), _ptr(k), int(words), _ptr(rx), _ptr(ry)),
+                    "bjj_mul_scalar_wide_batch")
+        return rx, ry
+
     def fixed_base_batch(self, scalars):
         k = _as_u8(scalars, 32)
         outs = [np.empty_like(k) for _ in range(2)]
@@ -193,8 +203,8 @@ class Engine:
 
     def poseidon_batch(self, inputs):
         ins = [_as_u8(v, 32) for v in inputs]
-        if not 1 <= len(ins) <= 8:
-            raise ValueError("invalid inputs length")       # poseidon-rs: Err on 0 or > 8 inputs
+        if not 1 <= len(ins) <= 6:
+            raise ValueError("Wrong inputs length")         # poseidon-rs 0.0.8: Err on 0 or more than 6 inputs
         arr = (ctypes.c_void_p * len(ins))(*[v.ctypes.data for v in ins])
         out = np.empty_like(ins[0])
         self._check(self.lib.bjj_poseidon_batch(self.ctx, len(ins), len(ins[0]), arr, _ptr(out)), "bjj_poseidon_batch")
@@ -259,11 +269,7 @@ class Point:
         return PointProjective(self.x, self.y, 1)
 
     def mul_scalar(self, n):
-        n = abs(int(n))                                  # src/lib.rs:156 drops the sign
-        if n >> 256:
-            raise ValueError("scalar wider than 256 bits: reduce on the host (mod ORDER, on-curve points only)")
-        rx, ry = default_engine().mul_scalar_batch(ints_to_le32([self.x]), ints_to_le32([self.y]), ints_to_le32([n]))
-        return Point(le32_to_ints(rx)[0], le32_to_ints(ry)[0])
+        return mul_scalar_batch([self], [n])[0]
 
     def compress(self):
         return default_engine().compress_batch(ints_to_le32([self.x]), ints_to_le32([self.y])).tobytes()
@@ -370,11 +376,17 @@ def verify(pk, sig, msg):
         return False
     if msg < 0:
         raise ValueError("negative msg (the reference panics in Fr::from_str)")
-    if sig.s >> 256:
-        raise ValueError("S wider than 256 bits")
     eng = default_engine()
-    ok = eng.verify_batch(*[ints_to_le32([v]) for v in (sig.r_b8.x, sig.r_b8.y, sig.s, pk.x, pk.y, msg)])
+    ok = eng.verify_batch(*[ints_to_le32([v]) for v in (sig.r_b8.x, sig.r_b8.y, _verify_scalar(sig.s), pk.x, pk.y, msg)])
     return bool(ok[0])
+
+
+def _verify_scalar(s):
+    """S as it crosses the 256-bit ABI.  The reference evaluates B8.mul_scalar(S) on the BigInt as given (sign dropped,
+    src/lib.rs:156, :405); B8 has order SUBORDER, so a wider S is reduced mod SUBORDER -- the same group element.
+    Scalars below 2^256 go through unreduced (the device handles them, S + SUBORDER included)."""
+    s = abs(int(s))
+    return s if s < (1 << 256) else s % SUBORDER
 
 
 def schnorr_hash(pk, msg, c):
@@ -399,9 +411,21 @@ def verify_schnorr(pk, m, r, s):
 
 # ---- batch entry points named by the north star ------------------------------------------------------
 def mul_scalar_batch(points, scalars, engine=None):
+    """Point::mul_scalar over a batch (src/lib.rs:149-164): scalars are BigInts of any size, the sign is dropped (:156).
+    Up to 256 bits they cross the ABI as they are; wider ones use the wide entry point (on-curve points: reduced mod
+    ORDER on the device; off-curve points: every bit replayed), up to 2048 bits."""
     eng = engine or default_engine()
-    rx, ry = eng.mul_scalar_batch(ints_to_le32([p.x for p in points]), ints_to_le32([p.y for p in points]),
-                                  ints_to_le32([abs(int(k)) for k in scalars]))
+    ks = [abs(int(k)) for k in scalars]
+    px, py = ints_to_le32([p.x for p in points]), ints_to_le32([p.y for p in points])
+    bits = max([k.bit_length() for k in ks] + [1])
+    if bits <= 256:
+        rx, ry = eng.mul_scalar_batch(px, py, ints_to_le32(ks))
+    else:
+        words = 8 * ((bits + 255) // 256)
+        if words > 64:
+            raise ValueError("scalars wider than 2048 bits are not supported by the device ABI")
+        buf = np.frombuffer(b"".join(k.to_bytes(4 * words, "little") for k in ks), dtype=np.uint8).reshape(-1, 4 * words)
+        rx, ry = eng.mul_scalar_wide_batch(px, py, buf, words)
     return [Point(x, y) for x, y in zip(le32_to_ints(rx), le32_to_ints(ry))]
 
 
@@ -425,7 +449,7 @@ def verify_batch(pks, sigs, msgs, engine=None):
     # msg > Q is `false` in the reference; clamp such messages to an all-ones word (still > Q) so they fit 32 bytes
     mm = [int(m) if int(m) <= Q else (1 << 256) - 1 for m in msgs]
     ok = eng.verify_batch(ints_to_le32([s.r_b8.x for s in sigs]), ints_to_le32([s.r_b8.y for s in sigs]),
-                          ints_to_le32([s.s for s in sigs]), ints_to_le32([p.x for p in pks]),
+                          ints_to_le32([_verify_scalar(s.s) for s in sigs]), ints_to_le32([p.x for p in pks]),
                           ints_to_le32([p.y for p in pks]), ints_to_le32(mm))
     return [bool(v) for v in ok]
 

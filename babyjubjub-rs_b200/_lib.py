@@ -49,6 +49,9 @@ for _name in [k for k in SIGNATURES if k.endswith("_batch")]:
     _res, _args = SIGNATURES[_name]
     SIGNATURES[_name + "_dev"] = (_res, list(_args) + [ctypes.c_void_p])
 
+SIGNATURES["bjj_mul_scalar_wide_batch"] = (_int, [_ctx, _sz, _u8p, _u8p, _u8p, _int, _u8p, _u8p])
+SIGNATURES["bjj_mul_scalar_wide_batch_dev"] = (_int, [_ctx, _sz, _u8p, _u8p, _u8p, _int, _u8p, _u8p, ctypes.c_void_p])
+
 # multi-device layer (one caller, one host batch, N devices); host pointers only
 _multi = ctypes.c_void_p
 SIGNATURES.update({

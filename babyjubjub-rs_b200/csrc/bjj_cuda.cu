@@ -111,6 +111,8 @@ struct Workspace {
     size_t proj_lanes;
     uint8_t* vs;             // verify scratch: hm, u, v, w + decompressed R8, A (8 x 32 B per lane)
     size_t vs_lanes;
+    uint8_t* kred;           // wide scalars reduced mod ORDER (32 B per lane)
+    size_t kred_lanes;
     cudaStream_t aux;        // side stream: the exact-lane kernel overlaps the fast EC kernel
     cudaEvent_t ev_fork, ev_join;
 };
@@ -142,6 +144,8 @@ struct bjj_ctx {
     unsigned long long launches;
     cudaError_t last;
     bool verify_split;          // half-size scalars in verify (split.cuh); BJJ_VERIFY_SPLIT=0 turns it off
+    size_t lane_hint;           // host flavour: the largest chunk of the running call, so that lane-sized scratch is
+                                // allocated ONCE up front (a cudaFree in mid-pipeline is a device-wide synchronisation)
 };
 
 #define CU(ctx, call)                      \
@@ -184,6 +188,7 @@ static int ensure_table(bjj_ctx* ctx, Workspace* ws, size_t slots) {
 static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, ExactQueue* q, ExactQueue* q2 = nullptr) {
     // 32 bytes: the two queue counters, then (at byte 16) the two lane-claim counters of the verify kernels
     if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, 32));
+    if (n < ctx->lane_hint) n = ctx->lane_hint;
     if (ws->exact_cap < n) {
         if (ws->exact_list) cudaFree(ws->exact_list);
         ws->exact_list = nullptr;
@@ -207,6 +212,7 @@ static unsigned long long* work_counters(Workspace* ws) { return reinterpret_cas
 #define BJJ_POINT_SUBBATCH ((size_t)1 << 21)
 
 static int ensure_proj(bjj_ctx* ctx, Workspace* ws, size_t lanes, ProjScratch* scr) {
+    if (lanes < ctx->lane_hint) lanes = ctx->lane_hint;
     if (ws->proj_lanes < lanes) {
         if (ws->proj) cudaFree(ws->proj);
         ws->proj = nullptr;
@@ -248,6 +254,7 @@ static void free_workspace(Workspace* ws) {
     if (ws->table) cudaFree(ws->table);
     if (ws->proj) cudaFree(ws->proj);
     if (ws->vs) cudaFree(ws->vs);
+    if (ws->kred) cudaFree(ws->kred);
     if (ws->exact_count) cudaFree(ws->exact_count);
     if (ws->exact_list) cudaFree(ws->exact_list);
     memset(ws, 0, sizeof(*ws));
@@ -418,11 +425,14 @@ int bjj_sync(bjj_ctx* ctx) {
 
 // `table`/`table_slots` select the per-thread window-table workspace (ctx-wide for _dev calls, per
 // pipeline slot for host calls).
-static int launch_mul_scalar(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
+// k_words = 8: plain 256-bit scalars.  Wider (multiples of 8 words): the on-curve lanes use the scalar reduced mod ORDER
+// (k_reduce_scalars), the off-curve lanes replay every bit of the wide scalar.
+static int launch_mul_scalar(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k, int k_words,
                              uint8_t* rx, uint8_t* ry, cudaStream_t st, Workspace* ws) {
     for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
         const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
         const size_t o = 32 * off;
+        const uint8_t* kw = k + (size_t)4 * k_words * off;
         int grid = grid_cap(ctx, bjjk::mul_scalar_blocks_per_sm(), m);
         int rc = ensure_table(ctx, ws, (size_t)grid * BJJ_BLOCK);
         if (rc) return rc;
@@ -432,13 +442,28 @@ static int launch_mul_scalar(bjj_ctx* ctx, size_t n, const uint8_t* px, const ui
         ProjScratch scr;
         rc = ensure_proj(ctx, ws, m < BJJ_POINT_SUBBATCH && n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &scr);
         if (rc) return rc;
-        bjjk::mul_scalar(grid, st, m, px + o, py + o, k + o, scr, ws->table, q, ctx->flags_dev);
+        const uint8_t* kfast = kw;
+        if (k_words > 8) {
+            const size_t want = m < ctx->lane_hint ? ctx->lane_hint : m;
+            if (ws->kred_lanes < want) {
+                if (ws->kred) cudaFree(ws->kred);
+                ws->kred = nullptr;
+                ws->kred_lanes = 0;
+                CU(ctx, cudaMalloc(&ws->kred, want * 32));
+                ws->kred_lanes = want;
+            }
+            bjjk::reduce_scalars(grid_cap(ctx, 8, m), st, m, kw, k_words, ws->kred);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+            kfast = ws->kred;
+        }
+        bjjk::mul_scalar(grid, st, m, px + o, py + o, kfast, scr, ws->table, q, ctx->flags_dev);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         k_batch_affine<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr, rx + o, ry + o);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        bjjk::mul_scalar_exact(ctx->sms * 4, st, px + o, py + o, k + o, rx + o, ry + o, q);
+        bjjk::mul_scalar_exact(ctx->sms * 4, st, px + o, py + o, kw, k_words, rx + o, ry + o, q);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
     }
@@ -490,6 +515,7 @@ static int launch_decompress(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_
 // verify scratch: four planes hm | u | v | w (32 B / lane each; u, v, w are the Straus scalars, see split.cuh)
 // and, for the compressed pipeline, the four decompressed coordinates
 static int ensure_vscratch(bjj_ctx* ctx, Workspace* ws, size_t lanes, uint8_t** hm, uint8_t** pts) {
+    if (lanes < ctx->lane_hint) lanes = ctx->lane_hint;
     if (ws->vs_lanes < lanes) {
         if (ws->vs) cudaFree(ws->vs);
         ws->vs = nullptr;
@@ -593,7 +619,11 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         uint8_t *dx = pts, *dy = pts + L, *dax = pts + 2 * L, *day = pts + 3 * L;
         // phase 0: decompress R8 (first half of each 64-byte signature) and A with one shared inversion pass
         ProjScratch scr;
-        rc = ensure_proj(ctx, ws, 2 * (n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m), &scr);
+        {
+            size_t lanes = n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m;
+            if (lanes < ctx->lane_hint) lanes = ctx->lane_hint;
+            rc = ensure_proj(ctx, ws, 2 * lanes, &scr);       // R8 and A share one inversion pass: two slots per lane
+        }
         if (rc) return rc;
         const int grid_p = grid_for(ctx, (const void*)k_decompress_prepare, m);
         const int grid_f = grid_for(ctx, (const void*)k_decompress_finish, m);
@@ -623,7 +653,7 @@ static int launch_poseidon(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* 
                            cudaStream_t st) {
     PoseidonIn pin;
     for (int j = 0; j < 8; j++) pin.p[j] = j < n_inputs ? in[j] : nullptr;
-    if (n_inputs < 1 || n_inputs > 8) return BJJ_ERR_ARG;
+    if (n_inputs < 1 || n_inputs > BJJ_POSEIDON_MAX_INPUTS) return BJJ_ERR_ARG;
     bjjk::poseidon(n_inputs + 1, grid_cap(ctx, bjjk::poseidon_blocks_per_sm(n_inputs + 1), n), st, n, pin, out, ctx->flags_dev);
     DEV_EPILOGUE
 }
@@ -667,7 +697,14 @@ int bjj_mul_scalar_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const ui
                              uint8_t* rx, uint8_t* ry, void* stream) {
     DEV_PROLOGUE
     if (!px || !py || !scalar32 || !rx || !ry) return BJJ_ERR_ARG;
-    return launch_mul_scalar(ctx, n, px, py, scalar32, rx, ry, st, &ctx->ws);
+    return launch_mul_scalar(ctx, n, px, py, scalar32, 8, rx, ry, st, &ctx->ws);
+}
+
+int bjj_mul_scalar_wide_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar, int scalar_words,
+                                  uint8_t* rx, uint8_t* ry, void* stream) {
+    DEV_PROLOGUE
+    if (!px || !py || !scalar || !rx || !ry || scalar_words < 8 || scalar_words > BJJ_MAX_SCALAR_WORDS || (scalar_words & 7)) return BJJ_ERR_ARG;
+    return launch_mul_scalar(ctx, n, px, py, scalar, scalar_words, rx, ry, st, &ctx->ws);
 }
 
 int bjj_fixed_base_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry, void* stream) {
@@ -713,7 +750,7 @@ int bjj_decompress_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_
 
 int bjj_poseidon_batch_dev(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out, void* stream) {
     DEV_PROLOGUE
-    if (!in || !out || n_inputs < 1 || n_inputs > 8) return BJJ_ERR_ARG;
+    if (!in || !out || n_inputs < 1 || n_inputs > BJJ_POSEIDON_MAX_INPUTS) return BJJ_ERR_ARG;
     for (int j = 0; j < n_inputs; j++)
         if (!in[j]) return BJJ_ERR_ARG;
     return launch_poseidon(ctx, n_inputs, n, in, out, st);
@@ -773,6 +810,12 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
     for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
     int rc = BJJ_OK;
     int which = 0;
+    // verify_compressed parks two points per lane in the projective scratch: the hint covers the larger user
+    ctx->lane_hint = cap <= 2 * BJJ_POINT_SUBBATCH ? cap : 0;
+    struct HintReset {
+        bjj_ctx* c;
+        ~HintReset() { c->lane_hint = 0; }
+    } hint_reset{ctx};
     // BJJ_PIPE_TIMING=1: per-chunk timeline (ms since the call started) on stderr -- diagnosis only
     static const bool pipe_timing = getenv("BJJ_PIPE_TIMING") != nullptr;
     struct Mark { cudaEvent_t in, comp, out; size_t lanes; };
@@ -820,7 +863,12 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         }
         CU(ctx, cudaStreamWaitEvent(comp.stream, sl.ev_in, 0));
         rc = launch(m, dptr, comp);
-        if (rc) return rc;
+        if (rc) {
+            // copies and kernels of earlier chunks may still be in flight against the caller's buffers: drain them
+            // before handing the buffers back
+            bjj_sync(ctx);
+            return rc;
+        }
         if (mark) cudaEventRecord(marks[nmarks].comp, comp.stream);
         CU(ctx, cudaEventRecord(sl.ev_out, comp.stream));
         CU(ctx, cudaStreamWaitEvent(sl.stream, sl.ev_out, 0));
@@ -906,7 +954,16 @@ int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
     return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
-        return launch_mul_scalar(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.ws);
+        return launch_mul_scalar(ctx, m, d[0], d[1], d[2], 8, d[3], d[4], sl.stream, &sl.ws);
+    });
+}
+
+int bjj_mul_scalar_wide_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar, int scalar_words,
+                              uint8_t* rx, uint8_t* ry) {
+    if (!ctx || scalar_words < 8 || scalar_words > BJJ_MAX_SCALAR_WORDS || (scalar_words & 7)) return BJJ_ERR_ARG;
+    HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar, (size_t)4 * scalar_words), H_OUT(rx, 32), H_OUT(ry, 32)};
+    return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
+        return launch_mul_scalar(ctx, m, d[0], d[1], d[2], scalar_words, d[3], d[4], sl.stream, &sl.ws);
     });
 }
 
@@ -963,7 +1020,7 @@ int bjj_decompress_batch(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* r
 }
 
 int bjj_poseidon_batch(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out) {
-    if (!ctx || !in || n_inputs < 1 || n_inputs > 8) return BJJ_ERR_ARG;
+    if (!ctx || !in || n_inputs < 1 || n_inputs > BJJ_POSEIDON_MAX_INPUTS) return BJJ_ERR_ARG;
     HostArg args[9];
     for (int j = 0; j < n_inputs; j++) args[j] = H_IN(in[j], 32);
     args[n_inputs] = H_OUT(out, 32);

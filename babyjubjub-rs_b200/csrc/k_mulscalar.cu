@@ -18,9 +18,14 @@ __global__ void __launch_bounds__(BJJ_BLOCK, BJJ_MULSCALAR_MINB) k_mul_scalar(si
     BJJ_FLAGS_END(gflags)
 }
 
-__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* k,
+__global__ void __launch_bounds__(BJJ_EXACT_BLOCK) k_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* k, int k_words,
                                                                       uint8_t* rx, uint8_t* ry, ExactQueue q) {
-    BJJ_QUEUE_LOOP(q) lane_mul_scalar_exact(px, py, k, rx, ry, q.list[j]);
+    BJJ_QUEUE_LOOP(q) lane_mul_scalar_exact(px, py, k, k_words, rx, ry, q.list[j]);
+}
+
+// wide scalars (more than 256 bits) -> scalar mod ORDER for the fast ladder of the on-curve lanes
+__global__ void __launch_bounds__(BJJ_BLOCK) k_reduce_scalars(size_t n, const uint8_t* wide, int k_words, uint8_t* out32) {
+    BJJ_LANE_LOOP(n) lane_reduce_scalar_order(wide, k_words, out32, i);
 }
 
 namespace bjjk {
@@ -35,9 +40,12 @@ void mul_scalar(int grid, cudaStream_t st, size_t n, const uint8_t* px, const ui
                 U128* table, ExactQueue q, uint32_t* gflags) {
     k_mul_scalar<<<grid, BJJ_BLOCK, 0, st>>>(n, px, py, k, scr, table, q, gflags);
 }
-void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_t* py, const uint8_t* k, uint8_t* rx,
+void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_t* py, const uint8_t* k, int k_words, uint8_t* rx,
                       uint8_t* ry, ExactQueue q) {
-    k_mul_scalar_exact<<<grid, BJJ_EXACT_BLOCK, 0, st>>>(px, py, k, rx, ry, q);
+    k_mul_scalar_exact<<<grid, BJJ_EXACT_BLOCK, 0, st>>>(px, py, k, k_words, rx, ry, q);
+}
+void reduce_scalars(int grid, cudaStream_t st, size_t n, const uint8_t* wide, int k_words, uint8_t* out32) {
+    k_reduce_scalars<<<grid, BJJ_BLOCK, 0, st>>>(n, wide, k_words, out32);
 }
 
 }  // namespace bjjk

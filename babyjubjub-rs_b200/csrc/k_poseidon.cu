@@ -1,4 +1,5 @@
-// poseidon_batch kernels, t = 2..9 (reference: POSEIDON.hash, poseidon-rs 0.0.8 behind src/lib.rs:59).
+// poseidon_batch kernels, t = 2..7 (reference: POSEIDON.hash, poseidon-rs 0.0.8 behind src/lib.rs:59; that crate's hash()
+// rejects an empty input and more than 6 inputs -- `inp.len() >= n_rounds_p.len() - 1` with its 8-entry round table).
 #include "kernels.h"
 
 using namespace bjj;
@@ -27,9 +28,7 @@ int poseidon_blocks_per_sm(int t) {
         case 4: return occ_t<4>();
         case 5: return occ_t<5>();
         case 6: return occ_t<6>();
-        case 7: return occ_t<7>();
-        case 8: return occ_t<8>();
-        default: return occ_t<9>();
+        default: return occ_t<7>();
     }
 }
 
@@ -40,9 +39,7 @@ void poseidon(int t, int grid, cudaStream_t st, size_t n, PoseidonIn in, uint8_t
         case 4: k_poseidon<4><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
         case 5: k_poseidon<5><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
         case 6: k_poseidon<6><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
-        case 7: k_poseidon<7><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
-        case 8: k_poseidon<8><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
-        default: k_poseidon<9><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
+        default: k_poseidon<7><<<grid, BJJ_BLOCK, 0, st>>>(n, in, out, gflags); break;
     }
 }
 

@@ -447,16 +447,48 @@ BJJ_HD void lane_mul_scalar(const uint8_t* px, const uint8_t* py, const uint8_t*
     store_ext_scratch(scr, i, acc);
 }
 
-// exact lane of mul_scalar: lane index taken from the queue
-BJJ_HD void lane_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, uint8_t* rx,
+// Scalars wider than 256 bits (the reference's n is a BigInt of any size): element i of a wide array is `nwords`
+// 32-bit little-endian words, nwords a multiple of 8 up to BJJ_MAX_SCALAR_WORDS.
+#define BJJ_MAX_SCALAR_WORDS 64
+
+// out = x mod ORDER for a wide x: on-curve points have order dividing ORDER = 8 * SUBORDER, so the fast ladder may use
+// the reduced scalar (exact).  Shift-and-subtract, MSB first; ORDER < 2^254, so 2 * acc + 1 fits 256 bits.
+BJJ_HD void lane_reduce_scalar_order(const uint8_t* wide, int nwords, uint8_t* out32, size_t i) {
+    uint32_t acc[8], t[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0;
+#pragma unroll 1
+    for (int blk = (nwords >> 3) - 1; blk >= 0; blk--) {
+        uint32_t w[8];
+        load_u256(w, wide, i * (size_t)(nwords >> 3) + (size_t)blk);
+#pragma unroll 1
+        for (int bit = 255; bit >= 0; bit--) {
+            uint32_t b = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) b = ((bit >> 5) == j) ? w[j] : b;
+            b = (b >> (bit & 31)) & 1u;
+#pragma unroll
+            for (int k = 7; k > 0; k--) acc[k] = (acc[k] << 1) | (acc[k - 1] >> 31);
+            acc[0] = (acc[0] << 1) | b;
+            const uint32_t borrow = sub256(t, acc, BJJ_ORDER);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = borrow ? acc[k] : t[k];
+        }
+    }
+    store_u256(out32, i, acc);
+}
+
+// exact lane of mul_scalar: lane index taken from the queue; the scalar is read at its full width
+BJJ_HD void lane_mul_scalar_exact(const uint8_t* px, const uint8_t* py, const uint8_t* scalar, int nwords, uint8_t* rx,
                                   uint8_t* ry, size_t i) {
     uint32_t flags = 0;
     PointAff p, r;
     load_fr(p.x, px, i, flags);
     load_fr(p.y, py, i, flags);
-    uint32_t n[8];
-    load_u256(n, scalar, i);
-    mul_scalar_exact(r, p, n, 8);
+    uint32_t n[BJJ_MAX_SCALAR_WORDS];
+#pragma unroll 1
+    for (int b = 0; b < (nwords >> 3); b++) load_u256(n + 8 * b, scalar, i * (size_t)(nwords >> 3) + (size_t)b);
+    mul_scalar_exact(r, p, n, nwords);
     store_fr(rx, i, r.x);
     store_fr(ry, i, r.y);
 }

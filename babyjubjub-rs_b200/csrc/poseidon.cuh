@@ -31,8 +31,6 @@ BJJ_POSEIDON_TABLES(4)
 BJJ_POSEIDON_TABLES(5)
 BJJ_POSEIDON_TABLES(6)
 BJJ_POSEIDON_TABLES(7)
-BJJ_POSEIDON_TABLES(8)
-BJJ_POSEIDON_TABLES(9)
 
 BJJ_HD void fr_pow5(Fr& x) {
     Fr x2, x4;

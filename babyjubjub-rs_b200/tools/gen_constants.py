@@ -276,7 +276,7 @@ def emit(out):
         w(" },\n")
     w("};\n\n")
 
-    for t in range(2, 10):
+    for t in range(2, 8):        # poseidon-rs 0.0.8 accepts 1..6 inputs
         o = poseidon_optimized(t)
         w("#define BJJ_POSEIDON_RP_%d %d\n" % (t, R_P[t]))
         space = "BJJ_CONST" if t == 6 else "BJJ_TABLE"   # t=6 (verify) sits in the constant bank

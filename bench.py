@@ -745,13 +745,11 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
                 "unit": "points/s", "ms_per_step": ms, "roofline_frac_imad": rate * 345 * FMUL / imad_peak, "oracle_checked_lanes": 1024})
 
     # POSEIDON.hash, every width poseidon-rs accepts (row a8 + next row f-2): t = n_inputs + 1
-    rounds_p = [56, 57, 56, 60, 60, 63, 64, 63]          # poseidon-rs / circomlib R_P for t = 2..9 (R_F = 8)
-    ins_all = [ax[:n], ay[:n], r8x[:n], r8y[:n], msgs[:n], dx, dy, s[:n]]
+    rounds_p = [56, 57, 56, 60, 60, 63]                  # poseidon-rs / circomlib R_P for t = 2..7 (R_F = 8)
+    ins_all = [ax[:n], ay[:n], r8x[:n], r8y[:n], msgs[:n], dx]
     ho = torch.empty((n, 32), dtype=torch.uint8, device=dev)
-    for nin in range(1, 9):
+    for nin in range(1, 7):
         ins = [t.contiguous() for t in ins_all[:nin]]
-        if nin == 8:
-            ins[7] = msgs[:n].flip(0).contiguous()          # S may exceed Q; Poseidon inputs must be field elements
         arr = (ctypes.c_void_p * nin)(*[t.data_ptr() for t in ins])
         ms = timed(lambda: lib.bjj_poseidon_batch_dev(ctx, nin, n, arr, dptr(ho), sp), max(2, args.steps // 2), warmup=1)
         eh = ora.poseidon([t[:128].cpu().numpy() for t in ins])

@@ -63,6 +63,8 @@ typedef struct bjj_ctx bjj_ctx;
 #define BJJ_FR_INV 3
 #define BJJ_FR_SQR 4
 
+#define BJJ_POSEIDON_MAX_INPUTS 6   /* poseidon-rs 0.0.8: t = n_inputs + 1 <= 7 */
+
 /* ---- context ------------------------------------------------------------------------------- */
 int bjj_device_count(void);
 int bjj_init(int device, bjj_ctx** out);      /* builds the B8 comb table on the device */
@@ -117,6 +119,15 @@ int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_
 int bjj_mul_scalar_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py,
                              const uint8_t* scalar32, uint8_t* rx, uint8_t* ry, void* stream);
 
+/* The same for BigInt scalars wider than 256 bits (src/lib.rs:149-164 loops over n.bits() of a BigInt of any size):
+ * scalar i is `scalar_words` 32-bit little-endian words at byte offset 4*scalar_words*i, 8 <= scalar_words <= 64, a
+ * multiple of 8.  On-curve points: the scalar is reduced mod ORDER on the device (exact: their order divides ORDER).
+ * Off-curve points: every bit is replayed like the reference does. */
+int bjj_mul_scalar_wide_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar,
+                              int scalar_words, uint8_t* rx, uint8_t* ry);
+int bjj_mul_scalar_wide_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar,
+                                  int scalar_words, uint8_t* rx, uint8_t* ry, void* stream);
+
 /* ---- B8.mul_scalar(k) (src/lib.rs:305, :329, :405): fixed-base comb ----------------------------- */
 int bjj_fixed_base_batch(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry);
 int bjj_fixed_base_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry, void* stream);
@@ -143,7 +154,9 @@ int bjj_decompress_batch(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* r
 int bjj_decompress_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_t* rx, uint8_t* ry,
                              uint8_t* status, void* stream);
 
-/* ---- POSEIDON.hash (poseidon-rs 0.0.8 behind src/lib.rs:59,333,370,401): n_inputs in 1..8,
+/* ---- POSEIDON.hash (poseidon-rs 0.0.8 behind src/lib.rs:59,333,370,401): n_inputs in 1..BJJ_POSEIDON_MAX_INPUTS --
+ *      the widths that crate accepts (its hash() returns Err("Wrong inputs length") for 0 or more than 6 inputs);
+ *      other counts return BJJ_ERR_ARG,
  *      in[j] = array of the j-th input of every lane (host flavour: host array of host pointers;
  *      dev flavour: host array of device pointers). ------------------------------------------------ */
 int bjj_poseidon_batch(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* const* in, uint8_t* out);

@@ -246,8 +246,10 @@ def blake512(data):
 # ---- Poseidon (poseidon-rs 0.0.8; call sites src/lib.rs:333,370,401) ---------------------------
 def poseidon(inputs):
     n = len(inputs)
-    if n == 0 or n > 8:
-        raise ValueError("invalid inputs length")
+    # poseidon-rs 0.0.8 hash(): `if inp.is_empty() || inp.len() >= self.constants.n_rounds_p.len() - 1` with an 8-entry
+    # round table, i.e. 1..6 inputs (t <= 7) [memory; the crate is not vendored -- ADVICE round 1]
+    if n == 0 or n > 6:
+        raise ValueError("Wrong inputs length")
     t = n + 1
     C, M = _pc.constants(t)
     r_p = _pc.R_P_TABLE[t - 2]

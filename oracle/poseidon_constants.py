@@ -74,6 +74,14 @@ def generate(t):
         return consts, M
 
 
+# What pins each width (t = inputs + 1).  poseidon-rs 0.0.8 accepts 1..6 inputs, so t = 2..7 is all the product offers.
+#   reference-held     : t = 6 -- the reference's own known-answer test (src/lib.rs:688-738) depends on one full
+#                        t = 6 evaluation through the signature S, and `verify == true` on it.
+#   third-party, recalled (tests/golden/poseidon_thirdparty.json; go-iden3-crypto poseidon_test.go and circomlib's
+#                        poseidon tests -- written down from memory, then CONFIRMED by this generator reproducing
+#                        all 77 digits of every one of them): t = 2, 3, 5, 6, 7.
+#   generator + published round table only: t = 4 (three inputs).  Same Grain-LFSR code path as the pinned widths;
+#                        the only width-specific input is R_P(4) = 56 from the table above.
 # Anchors (these equal circomlib's poseidon_constants.json entries).
 ANCHORS = {
     2: {"C0": 0x09c46e9ec68e9bd4fe1faaba294cba38a71aa177534cdd1b6c7dc0dbd0abd7a7},

@@ -7,6 +7,10 @@ use std::os::raw::{c_char, c_int, c_void};
 pub struct bjj_ctx {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct bjj_multi {
+    _private: [u8; 0],
+}
 
 pub const BJJ_OK: c_int = 0;
 pub const BJJ_ERR_CUDA: c_int = 1;
@@ -45,6 +49,9 @@ extern "C" {
     // Point::mul_scalar (src/lib.rs:149-164)
     pub fn bjj_mul_scalar_batch(ctx: *mut bjj_ctx, n: usize, px: *const u8, py: *const u8, scalar32: *const u8,
                                 rx: *mut u8, ry: *mut u8) -> c_int;
+    // the same for BigInt scalars wider than 256 bits (scalar_words x 32-bit words per lane)
+    pub fn bjj_mul_scalar_wide_batch(ctx: *mut bjj_ctx, n: usize, px: *const u8, py: *const u8, scalar: *const u8,
+                                     scalar_words: c_int, rx: *mut u8, ry: *mut u8) -> c_int;
     // B8.mul_scalar (src/lib.rs:305,329,405)
     pub fn bjj_fixed_base_batch(ctx: *mut bjj_ctx, n: usize, scalar32: *const u8, rx: *mut u8, ry: *mut u8) -> c_int;
     // PrivateKey::public / scalar_key / sign (src/lib.rs:284-342)
@@ -67,4 +74,22 @@ extern "C" {
     // decompress_signature + decompress_point + verify (src/lib.rs:260-268)
     pub fn bjj_verify_compressed_batch(ctx: *mut bjj_ctx, n: usize, sig64: *const u8, pk32: *const u8,
                                        msg32: *const u8, ok: *mut u8, status: *mut u8) -> c_int;
+
+    // one caller, one host batch, N devices (BASELINE config 4); no reference counterpart
+    pub fn bjj_multi_init(n_devices: c_int, devices: *const c_int, out: *mut *mut bjj_multi) -> c_int;
+    pub fn bjj_multi_destroy(m: *mut bjj_multi);
+    pub fn bjj_multi_devices(m: *mut bjj_multi) -> c_int;
+    pub fn bjj_multi_ctx(m: *mut bjj_multi, i: c_int) -> *mut bjj_ctx;
+    pub fn bjj_multi_set_host_register(m: *mut bjj_multi, on: c_int);
+    pub fn bjj_multi_kernel_launches(m: *mut bjj_multi) -> u64;
+    pub fn bjj_multi_verify_batch(m: *mut bjj_multi, n: usize, r8x: *const u8, r8y: *const u8, s32: *const u8, ax: *const u8,
+                                  ay: *const u8, msg32: *const u8, ok: *mut u8) -> c_int;
+    pub fn bjj_multi_verify_compressed_batch(m: *mut bjj_multi, n: usize, sig64: *const u8, pk32: *const u8, msg32: *const u8,
+                                             ok: *mut u8, status: *mut u8) -> c_int;
+    pub fn bjj_multi_mul_scalar_batch(m: *mut bjj_multi, n: usize, px: *const u8, py: *const u8, scalar32: *const u8,
+                                      rx: *mut u8, ry: *mut u8) -> c_int;
+    pub fn bjj_multi_public_batch(m: *mut bjj_multi, n: usize, key32: *const u8, rx: *mut u8, ry: *mut u8) -> c_int;
+    pub fn bjj_multi_fixed_base_batch(m: *mut bjj_multi, n: usize, scalar32: *const u8, rx: *mut u8, ry: *mut u8) -> c_int;
+    pub fn bjj_multi_decompress_batch(m: *mut bjj_multi, n: usize, in32: *const u8, rx: *mut u8, ry: *mut u8,
+                                      status: *mut u8) -> c_int;
 }

@@ -46,7 +46,7 @@ def main():
                    "msg": str(c[5] & ((1 << 256) - 1)), "ok": oracle_verify(c)})
     out["verify"] = vf
     ps = []
-    for nin in range(1, 9):
+    for nin in range(1, 7):
         for ins in (list(range(1, nin + 1)), [0] * nin, [Q - 1] * nin, [rnd.randrange(Q) for _ in range(nin)]):
             ps.append({"in": [str(v) for v in ins], "out": str(O.poseidon(ins))})
     out["poseidon"] = ps

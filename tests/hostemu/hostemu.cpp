@@ -123,7 +123,7 @@ uint32_t emu_mul_scalar(size_t n, const uint8_t* px, const uint8_t* py, const ui
     ProjScratch scr = proj_scratch(n);
     for (size_t i = 0; i < n; i++) lane_mul_scalar(px, py, k, scr, i, lane_table(), q, flags);
     batch_affine(scr, rx, ry, n);
-    for (uint32_t j = 0; j < g_count; j++) lane_mul_scalar_exact(px, py, k, rx, ry, g_list[j]);
+    for (uint32_t j = 0; j < g_count; j++) lane_mul_scalar_exact(px, py, k, 8, rx, ry, g_list[j]);
     return flags;
 }
 
@@ -179,8 +179,6 @@ uint32_t emu_poseidon(int n_inputs, size_t n, const uint8_t* const* in, uint8_t*
             case 4: lane_poseidon<5>(in, out, i, flags); break;
             case 5: lane_poseidon<6>(in, out, i, flags); break;
             case 6: lane_poseidon<7>(in, out, i, flags); break;
-            case 7: lane_poseidon<8>(in, out, i, flags); break;
-            case 8: lane_poseidon<9>(in, out, i, flags); break;
             default: return 0x80000000u;
         }
     }

@@ -119,7 +119,7 @@ def check_compress_decompress(be, ref, n_random, seed=5):
     assert set(st) >= {0, 1, 3}
 
 
-def check_poseidon(be, ref, n, seed=6, widths=range(1, 9)):
+def check_poseidon(be, ref, n, seed=6, widths=range(1, 7)):
     rnd = random.Random(seed)
     for nin in widths:
         cols = [[rnd.randrange(Q) for _ in range(n)] for _ in range(nin)]

@@ -58,3 +58,17 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
                 assert "hostemu" not in text or f in ("fr.cuh",), f
+
+
+def test_rust_ffi_declares_every_host_flavour_symbol():
+    """rust/src/ffi.rs cannot be compiled here (no toolchain), but it can be read: every host-pointer entry point of
+    the header must have an `extern "C"` declaration there, and nothing that the header lacks."""
+    text = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (bjj_[a-z0-9_]+)\s*\(", text))
+    header = set(declared_symbols())
+    host = {s for s in header if not s.endswith("_dev")}
+    assert not (host - declared), sorted(host - declared)
+    assert not (declared - header), sorted(declared - header)
+    lib_rs = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
+    assert "unsafe impl Sync for Engine" not in lib_rs           # the C context is one-thread-at-a-time
+    assert "Mutex<Engine>" in lib_rs

@@ -18,7 +18,7 @@ def _gen():
 def test_poseidon_tables_agree():
     from oracle import poseidon_constants as pc
     g = _gen()
-    for t in (2, 3, 6, 9):
+    for t in (2, 3, 6, 7):
         rc, mds = g.poseidon_tables(t)
         C, M = pc.constants(t)
         assert rc == C and mds == M
@@ -52,6 +52,6 @@ def test_optimized_poseidon_schedule_equals_dense():
     import random
     g = _gen()
     rnd = random.Random(9)
-    for t in range(2, 10):
+    for t in range(2, 8):
         for ins in ([0] * (t - 1), list(range(1, t)), [rnd.randrange(Q) for _ in range(t - 1)]):
             assert g.poseidon_optimized_eval(ins) == O.poseidon(ins), t

@@ -390,3 +390,42 @@ def test_split_scalars_on_device(gpu, hostemu):
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     hostemu.lib.emu_split(ctypes.c_size_t(n), p(H), p(S), p(U), p(V), p(neg_h), p(W))
     assert np.array_equal(u, U) and np.array_equal(v, V) and np.array_equal(neg, neg_h) and np.array_equal(w, W)
+
+
+def test_wide_scalars_match_the_reference_bigint_semantics(gpu):
+    """The reference takes BigInt scalars of any size (src/lib.rs:149-164 loops over n.bits(); verify hands S to
+    B8.mul_scalar unreduced, :405).  On-curve points: a wide scalar acts mod the group order; off-curve points: every
+    bit of the wide scalar is replayed.  Checked against the integer oracle, which runs the literal loop."""
+    import random
+    bjj = gpu.bjj
+    rnd = random.Random(2024)
+    b8 = bjj.Point(*O.B8)
+    off = bjj.Point((O.B8[0] + 1) % O.Q, O.B8[1])            # x + 1: not on the curve
+    assert O.on_curve(O.B8) and not O.on_curve((off.x, off.y))
+    pts, ks = [], []
+    for bits in (257, 300, 511, 512, 1024, 2048):
+        for p in (b8, off, bjj.Point(0, 1), bjj.Point(0, 0)):
+            pts.append(p)
+            ks.append(rnd.getrandbits(bits) | (1 << (bits - 1)))
+    # mixed widths in one batch, a negative scalar (sign dropped, src/lib.rs:156) and a narrow one beside wide ones
+    pts += [b8, off, b8]
+    ks += [-(rnd.getrandbits(700)), 5, O.SUBORDER * 8 + 3]
+    got = bjj.mul_scalar_batch(pts, ks)
+    for p, k, g in zip(pts, ks, got):
+        ex, ey = O.mul_scalar((p.x, p.y), abs(k))
+        assert (g.x, g.y) == (ex, ey), (p, k.bit_length())
+    # single-point API with a wide scalar
+    k = rnd.getrandbits(900)
+    assert (lambda r: (r.x, r.y))(off.mul_scalar(k)) == O.mul_scalar((off.x, off.y), k)
+    # verify with S >= 2^256: same group element as S mod SUBORDER (B8 has order SUBORDER)
+    key = bytes(rnd.getrandbits(8) for _ in range(32))
+    msg = rnd.getrandbits(250)
+    (r8, s) = O.sign(key, msg)
+    pk = O.public(key)
+    for s_wide in (s + (1 << 256) * 7 * O.SUBORDER, s + O.SUBORDER * (1 << 300), -(s + O.SUBORDER * (1 << 260)), s + (1 << 256)):
+        exp = O.verify(pk, (r8, abs(s_wide)), msg)
+        got = bjj.verify(bjj.Point(*pk), bjj.Signature(bjj.Point(*r8), s_wide), msg)
+        assert got == exp, s_wide.bit_length()
+    oks = bjj.verify_batch([bjj.Point(*pk)] * 2, [bjj.Signature(bjj.Point(*r8), s + (O.SUBORDER << 270)),
+                                                    bjj.Signature(bjj.Point(*r8), s + (1 << 256))], [msg, msg])
+    assert oks == [True, O.verify(pk, (r8, s + (1 << 256)), msg)]
