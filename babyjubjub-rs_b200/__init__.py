@@ -31,7 +31,7 @@ SUBORDER = ORDER >> 3
 B8 = (5299619240641551281634865583518297030282874472190772894086521144482721001553,
       16950150798460657717958625567821834550301663161624707787222815936182638968203)
 
-FR_MUL, FR_ADD, FR_SUB, FR_INV, FR_SQR = 0, 1, 2, 3, 4
+FR_MUL, FR_ADD, FR_SUB, FR_INV, FR_SQR, FR_SQR_LAZY = 0, 1, 2, 3, 4, 5
 STATUS_STRINGS = {
     0: "",
     1: "y outside the Finite Field over R",

@@ -662,7 +662,7 @@ extern "C" {
 
 int bjj_fr_op_batch_dev(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, void* stream) {
     DEV_PROLOGUE
-    if (!a || !out || op < 0 || op > 4) return BJJ_ERR_ARG;
+    if (!a || !out || op < 0 || op > BJJ_FR_SQR_LAZY) return BJJ_ERR_ARG;
     if (!b) b = a;
     k_fr_op<<<grid_for(ctx, (const void*)k_fr_op, n), BJJ_BLOCK, 0, st>>>(op, n, a, b, out, ctx->flags_dev);
     DEV_EPILOGUE
@@ -907,7 +907,7 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
 extern "C" {
 
 int bjj_fr_op_batch(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
-    if (!ctx || !a || !out || op < 0 || op > 4) return BJJ_ERR_ARG;
+    if (!ctx || !a || !out || op < 0 || op > BJJ_FR_SQR_LAZY) return BJJ_ERR_ARG;
     if (!b) b = a;
     HostArg args[] = {H_IN(a, 32), H_IN(b, 32), H_OUT(out, 32)};
     return run_host(ctx, n, args, 3, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {

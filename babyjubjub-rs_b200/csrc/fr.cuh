@@ -351,9 +351,124 @@ BJJ_HD void fr_dot(Fr& r, const Fr* A, const Fr* B) {
     if (NP > 7) fr_cond_sub_2q(r);
 }
 
-// A dedicated squaring (28 doubled cross products + 8 squares + reduction = 100 wide MACs instead of 128) was
-// measured as a loss inside the kernels (tools/microbench/fr_sqr_proto.cuh, profiles/r1_imad_bench.jsonl).
-BJJ_HD void fr_sqr(Fr& r, const Fr& a) { fr_mul(r, a, a); }
+// ------------------------------------------------------------------------------------------------
+// Montgomery squaring: 36 + 64 wide MACs instead of 128
+// ------------------------------------------------------------------------------------------------
+
+// c[0..2N-1] += {a0..a(N-1)} * b (lo -> c[2k], hi -> c[2k+1]); TOP = 1: carry-out added into c[2N], 0: provably none.
+template <int N, int TOP>
+BJJ_HD void macn(uint32_t* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    static_assert(N >= 1 && N <= 4 && TOP >= 0 && TOP <= 1, "macn");
+#if BJJ_DEVICE_CODE
+    uint32_t t = TOP ? c[2 * N] : 0u;       // TOP = 0: a dead zero temporary, ptxas drops the addc
+    if (N == 1) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+            : "+r"(c[0]), "+r"(c[1]), "+r"(t) : "r"(a0), "r"(b));
+    } else if (N == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\taddc.u32 %4, %4, 0;"
+            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(t) : "r"(a0), "r"(a1), "r"(b));
+    } else if (N == 3) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\tmadc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\tmadc.hi.cc.u32 %5, %9, %10, %5;\n\taddc.u32 %6, %6, 0;"
+            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(t)
+            : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\tmadc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\taddc.u32 %8, %8, 0;"
+            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(t)
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+    }
+    if (TOP) c[2 * N] = t;
+#else
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    uint64_t carry = 0;
+    for (int k = 0; k < N; k++) {
+        uint64_t p = (uint64_t)a[k] * b;
+        uint64_t t = (uint64_t)c[2 * k] + (uint32_t)p + carry;
+        c[2 * k] = (uint32_t)t;
+        carry = t >> 32;
+        t = (uint64_t)c[2 * k + 1] + (p >> 32) + carry;
+        c[2 * k + 1] = (uint32_t)t;
+        carry = t >> 32;
+    }
+    if (TOP) c[2 * N] += (uint32_t)carry;
+#endif
+}
+
+// s + n + carry(sx + sy): the value of column I once the carry of column I-1 (sx + sy is 0 or 2^32) is folded in
+BJJ_HD uint32_t fold_sum(uint32_t s, uint32_t n, uint32_t sx, uint32_t sy) {
+#if BJJ_DEVICE_CODE
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %3, %4;\n\taddc.u32 %0, %1, %2;\n\t}" : "=r"(r) : "r"(s), "r"(n), "r"(sx), "r"(sy));
+    return r;
+#else
+    return s + n + (uint32_t)(((uint64_t)sx + sy) >> 32);
+#endif
+}
+
+// Row I of the squaring triangle,  a_I * (a_I + 2 * (a >> 32(I+1)) * 2^32)  at absolute column 2I, followed by the
+// reduction step of column I.  d[j] = limb j of 2a (j >= 2), c = a_(I+1) << 1 (the limb of 2 * (a >> 32(I+1)) that
+// takes no bit from below).  Products with j = I (mod 2) start at the even column 2I: always the X chain; the others
+// start at 2I + 1: always Y.  Column bound: after step I the total is < 2^(32(I+1)) * (2a + Q) < 2^(32(I+9)) because
+// 2a + Q < 5Q < 2^256, and X, Y are each <= the total.  The row's X chain ends at column I+7 (I even: its carry opens
+// the fresh X[I+8]) or I+8 (I odd: no carry-out); the Y chain the other way round.  The reduction chains are those of
+// BJJ_MUL_STEP, except that the carry of column I-1 enters with the reduction (nothing else starts at column I).
+#define BJJ_SQR_ROW(I, NX, NY, x1, x2, x3, y0, y1, y2, y3)                                              \
+    {                                                                                                   \
+        macn<NX, ((I) & 1) ? 0 : 1>(&X[2 * (I)], a.v[I], x1, x2, x3, a.v[I]);                           \
+        if (NY > 0) macn<(NY > 0 ? NY : 1), ((I) & 1) ? 1 : 0>(&Y[2 * (I) + 1], y0, y1, y2, y3, a.v[I]); \
+    }
+#define BJJ_SQR_REDC(S, N, I)                                                                           \
+    {                                                                                                   \
+        const uint32_t m = mont_m((I) ? fold_sum(S[I], N[I], X[(I) ? (I)-1 : 0], Y[(I) ? (I)-1 : 0]) : S[I] + N[I]); \
+        mac4<((I) > 0), 1>(&S[I], BJJ_Q0, BJJ_Q2, BJJ_Q4, BJJ_Q6, m, X[(I) ? (I)-1 : 0], Y[(I) ? (I)-1 : 0]); \
+        mac4<false, 0>(&N[I + 1], BJJ_Q1, BJJ_Q3, BJJ_Q5, BJJ_Q7, m);                                   \
+    }
+
+// r = a * a / 2^256 mod Q;  a in [0, 2Q)  ->  r in [0, 2Q)  (r < 4Q^2 / 2^256 + Q < 1.76 Q).  The same integer as
+// fr_mul_inline(r, a, a) up to a multiple of Q -- in fact identical: both return (a^2 + m Q) / 2^256 with the same m.
+BJJ_HD void fr_sqr_inline(Fr& r, const Fr& a) {
+    uint32_t X[18], Y[18], d[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 18; i++) X[i] = Y[i] = 0;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+        c[j] = a.v[j] << 1;
+        d[j] = (a.v[j] << 1) | (a.v[j - 1] >> 31);
+    }
+    BJJ_SQR_ROW(0, 4, 4, d[2], d[4], d[6], c[1], d[3], d[5], d[7])
+    BJJ_SQR_REDC(X, Y, 0)
+    BJJ_SQR_ROW(1, 4, 3, d[3], d[5], d[7], c[2], d[4], d[6], 0u)
+    BJJ_SQR_REDC(Y, X, 1)
+    BJJ_SQR_ROW(2, 3, 3, d[4], d[6], 0u, c[3], d[5], d[7], 0u)
+    BJJ_SQR_REDC(X, Y, 2)
+    BJJ_SQR_ROW(3, 3, 2, d[5], d[7], 0u, c[4], d[6], 0u, 0u)
+    BJJ_SQR_REDC(Y, X, 3)
+    BJJ_SQR_ROW(4, 2, 2, d[6], 0u, 0u, c[5], d[7], 0u, 0u)
+    BJJ_SQR_REDC(X, Y, 4)
+    BJJ_SQR_ROW(5, 2, 1, d[7], 0u, 0u, c[6], 0u, 0u, 0u)
+    BJJ_SQR_REDC(Y, X, 5)
+    BJJ_SQR_ROW(6, 1, 1, 0u, 0u, 0u, c[7], 0u, 0u, 0u)
+    BJJ_SQR_REDC(X, Y, 6)
+    BJJ_SQR_ROW(7, 1, 0, 0u, 0u, 0u, 0u, 0u, 0u, 0u)
+    BJJ_SQR_REDC(Y, X, 7)
+    fr_merge_xy(r, X, Y);
+}
+
+#ifndef BJJ_DEDICATED_SQR
+#define BJJ_DEDICATED_SQR 1
+#endif
+BJJ_HD void fr_sqr(Fr& r, const Fr& a) {
+#if BJJ_DEDICATED_SQR
+    fr_sqr_inline(r, a);
+#else
+    fr_mul(r, a, a);
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------
 // conversions and helpers

@@ -265,11 +265,15 @@ BJJ_HD void store_zero_scratch(const ProjScratch& s, size_t i) {
     store_u256(s.z, i, z.v);
 }
 
+// (A warp-cooperative variant of the inversion below -- prefix/suffix products across the 32 lanes by shuffles, one
+// Fermat inversion of the warp's total -- was measured and dropped: under SIMT the 32 per-thread inversions of a warp
+// already ARE one instruction stream, so sharing it buys nothing and the 12 extra multiplications cost: public_batch
+// 341 -> 322 M keys/s.  What amortises the inversion is lanes per thread.)
 BJJ_HD void batch_affine_strided(const ProjScratch& s, uint8_t* rx, uint8_t* ry, size_t n, size_t t, size_t T) {
-    if (t >= n) return;
     const Fr one = fr_const(BJJ_ONE_M);
     Fr acc = one, z;
     size_t last = t;
+    if (t >= n) return;
 #pragma unroll 1
     for (size_t i = t; i < n; i += T) {
         load_u256(z.v, s.z, i);
@@ -309,6 +313,7 @@ BJJ_HD void batch_affine_strided(const ProjScratch& s, uint8_t* rx, uint8_t* ry,
 #define BJJ_FR_OP_SUB 2
 #define BJJ_FR_OP_INV 3
 #define BJJ_FR_OP_SQR 4
+#define BJJ_FR_OP_SQR_LAZY 5
 BJJ_HD void lane_fr_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t i, uint32_t& flags) {
     Fr x, y, r;
     load_fr(x, a, i, flags);
@@ -318,6 +323,13 @@ BJJ_HD void lane_fr_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
         case BJJ_FR_OP_ADD: fr_add(r, x, y); break;
         case BJJ_FR_OP_SUB: fr_sub(r, x, y); break;
         case BJJ_FR_OP_INV: fr_inv(r, x); break;
+        case BJJ_FR_OP_SQR_LAZY: {      // the squaring on the upper half of the lazy domain: (x mod Q) + Q in [Q, 2Q)
+            const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+            fr_reduce(x);
+            add256(x.v, x.v, q);
+            fr_sqr(r, x);
+            break;
+        }
         default: fr_sqr(r, x); break;
     }
     store_fr(out, i, r);
@@ -628,10 +640,10 @@ BJJ_HD void lane_decompress_prepare(const uint8_t* in, size_t stride, size_t off
 
 // in-place inversion of scr.z[t], scr.z[t+T], ... (zeros stay zero); one Fermat inversion per thread
 BJJ_HD void batch_inverse_strided(const ProjScratch& s, size_t n, size_t t, size_t T) {
-    if (t >= n) return;
     const Fr one = fr_const(BJJ_ONE_M);
     Fr acc = one, z;
     size_t last = t;
+    if (t >= n) return;
 #pragma unroll 1
     for (size_t i = t; i < n; i += T) {
         load_u256(z.v, s.z, i);
@@ -764,13 +776,23 @@ BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, co
     fixed_base_comb(r8, comb, r);
     PointExt a;
     fixed_base_comb(a, comb, sk);
-    // affine coordinates of R8 and A on the original curve
-    PointProj pj;
+    // affine coordinates of R8 and A on the original curve: both Z are non-zero (complete formulas on curve points),
+    // so ONE inversion of Z_R * Z_A serves both
+    PointProj pr, pa;
     PointAff r8a, aa;
-    ext_to_proj(pj, r8);
-    proj_affine(r8a, pj);
-    ext_to_proj(pj, a);
-    proj_affine(aa, pj);
+    ext_to_proj(pr, r8);
+    ext_to_proj(pa, a);
+    {
+        Fr t, ti, zr, za;
+        fr_mul(t, pr.z, pa.z);
+        fr_inv(ti, t);
+        fr_mul(zr, ti, pa.z);
+        fr_mul(za, ti, pr.z);
+        fr_mul(r8a.x, pr.x, zr);
+        fr_mul(r8a.y, pr.y, zr);
+        fr_mul(aa.x, pa.x, za);
+        fr_mul(aa.y, pa.y, za);
+    }
     Fr st[6], mraw;
     fr_zero(st[0]);
     st[1] = r8a.x;
@@ -845,6 +867,7 @@ BJJ_HD void lane_sign(const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, 
 // (`a` is the public key and `r8` the commitment point in both).
 #define BJJ_MODE_EDDSA 0
 #define BJJ_MODE_SCHNORR 1
+#define BJJ_MODE_NEVER 0x5a5a5a5a   // no caller passes it: guards the pipe-selection ballast of vm.cuh
 BJJ_HD void verify_hm(Fr& hm, const PointAff& r8, const PointAff& a, const Fr& msg_m, int mode) {
     Fr st[6];
     fr_zero(st[0]);

@@ -95,9 +95,9 @@ __device__ __forceinline__ void set_identity(const Regs& s) {
 
 // acc = 2 acc   (dbl-2008-hwcd, a = -1: 4S + 3M, +1M for T; curve.cuh::ext_dbl)
 __device__ __forceinline__ void dbl(const Regs& s, bool want_t) {
-    mul2(s.t0, s.X, s.X, s.t1, s.Y, s.Y);        // xx, yy
+    sqr2(s.t0, s.X, s.t1, s.Y);                  // xx, yy
     add(s.t3, s.X, s.Y);
-    mul2(s.t2, s.Z, s.Z, s.t3, s.t3, s.t3);      // zz, (X+Y)^2
+    sqr2(s.t2, s.Z, s.t3, s.t3);                 // zz, (X+Y)^2
     addsub(s.t4, s.t1, s.t1, s.t0);              // H' = yy + xx, G = yy - xx
     sub(s.t3, s.t3, s.t4);                       // E = 2XY
     dblsub(s.t2, s.t2, s.t1);                    // F' = 2zz - G

@@ -46,9 +46,16 @@ def build(specs):
         os.makedirs(d, exist_ok=True)
         defs = ["-D" + m for m in macros.split(",") if m]
         obj = os.path.join(d, "k_verify.o")
-        subprocess.check_call([nvcc] + FLAGS + defs + ["-c", os.path.join(CSRC, "k_verify.cu"), "-o", obj], cwd=CSRC)
-        subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", os.path.join(d, "libbjj_cuda.so"), obj] +
-                              [os.path.join(OBJ, u + ".o") for u in OTHER_UNITS])
+        if name.startswith("all_"):                      # a variant named all_* rebuilds EVERY unit with the macros
+            from concurrent.futures import ThreadPoolExecutor
+            units = ["k_verify"] + OTHER_UNITS
+            with ThreadPoolExecutor(max_workers=len(units)) as ex:
+                list(ex.map(lambda u: subprocess.check_call([nvcc] + FLAGS + ["-diag-suppress", "177"] + defs + ["-c", os.path.join(CSRC, u + ".cu"), "-o", os.path.join(d, u + ".o")], cwd=CSRC), units))
+            subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", os.path.join(d, "libbjj_cuda.so")] + [os.path.join(d, u + ".o") for u in units])
+        else:
+            subprocess.check_call([nvcc] + FLAGS + defs + ["-c", os.path.join(CSRC, "k_verify.cu"), "-o", obj], cwd=CSRC)
+            subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", os.path.join(d, "libbjj_cuda.so"), obj] +
+                                  [os.path.join(OBJ, u + ".o") for u in OTHER_UNITS])
         res = subprocess.run(["cuobjdump", "-res-usage", obj], stdout=subprocess.PIPE, text=True).stdout.splitlines()
         regs = [ln.strip().split()[0] for prev, ln in zip(res, res[1:]) if "k_verify_ec" in prev]
         print("built %-12s %-40s k_verify_ec %s" % (name, " ".join(defs) or "(no macros)", regs[0] if regs else "?"))

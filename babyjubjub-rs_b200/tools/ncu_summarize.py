@@ -116,6 +116,13 @@ def main():
                     except ValueError:
                         pass
         total = sum(ex.values())
+        # ncu lists the instructions of some kernels once per inlining context: normalise the per-opcode counts to the
+        # kernel's own smsp__inst_executed.sum
+        raw_total = m.get("smsp__inst_executed.sum")
+        if total and raw_total and abs(total / raw_total - 1.0) > 0.01:
+            scale = raw_total / total
+            ex = collections.Counter({k: int(round(v * scale)) for k, v in ex.items()})
+            total = sum(ex.values())
         wide = ex.get("IMAD.WIDE", 0)
         light = sum(v for k, v in ex.items() if k in FMA_LIGHT)
         if total:

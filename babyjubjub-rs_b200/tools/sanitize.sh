@@ -1,0 +1,12 @@
+#!/bin/bash
+# compute-sanitizer over the GPU parity tests of the queue / table / shared-memory kernels.
+# Usage (on a GPU box):  bash babyjubjub-rs_b200/tools/sanitize.sh <out-dir>
+out=${1:-gpurun_out/sanitize}
+mkdir -p "$out"
+sel="test_verify or test_mul_scalar or test_split or test_schnorr or test_sign or test_fixed_base or test_wide or test_empty"
+for tool in memcheck racecheck synccheck initcheck; do
+  echo "== compute-sanitizer --tool $tool" | tee "$out/$tool.txt"
+  timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests -m gpu -x -q -k "$sel" >> "$out/$tool.txt" 2>&1
+  echo "exit=$?" >> "$out/$tool.txt"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|exit=" "$out/$tool.txt" | tail -4
+done

@@ -62,6 +62,7 @@ typedef struct bjj_ctx bjj_ctx;
 #define BJJ_FR_SUB 2
 #define BJJ_FR_INV 3
 #define BJJ_FR_SQR 4
+#define BJJ_FR_SQR_LAZY 5   /* a^2 computed on (a mod Q) + Q: the squaring on the upper half of the lazy domain */
 
 #define BJJ_POSEIDON_MAX_INPUTS 6   /* poseidon-rs 0.0.8: t = n_inputs + 1 <= 7 */
 

@@ -25,6 +25,8 @@ def check_fr(be, ref, n, seed=1):
     A, B = pack(a), pack(b)
     for op in (0, 1, 2, 4):
         _eq(be.fr_op(op, A, B), ref.fr_op(op, A, B), "fr op %d" % op)
+    # op 5: the dedicated squaring on inputs in [Q, 2Q) (lazy domain) must agree with the plain square
+    _eq(be.fr_op(5, A, B), ref.fr_op(4, A, B), "fr sqr on the lazy domain")
     m = min(n, 256)
     _eq(be.fr_op(3, A[:m], B[:m]), ref.fr_op(3, A[:m], B[:m]), "fr inverse")
     # spot-check the C oracle itself against Python integers
