@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(BJJ_VM_THREADS, BJJ_EC_VM_MINB) k_verify_ec_vm
     const vm::Table ta = vm::table_of(table, tslot), tr = vm::table_of(table, tslot + 1);
     BJJ_CLAIM_LOOP(n, work)
     if (i < n && ok[i] == BJJ_OK_PENDING) lane_verify_ec_vm(r8x, r8y, ax, ay, hm, plane, ok, i, ta, tr, comb, mode);
-    vm::fma_ballast(mode == BJJ_MODE_NEVER, (uint32_t)n, ok);      // never taken: see vm.cuh
+    fma_ballast(mode == BJJ_MODE_NEVER, (uint32_t)n, ok);      // never taken: see fr.cuh
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).

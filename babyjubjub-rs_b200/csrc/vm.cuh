@@ -139,29 +139,6 @@ static __device__ __noinline__ void addsub(Slot s, Slot d, Slot a, Slot b) {
     st(d, r);
 }
 
-// ---- pipe-selection ballast ----------------------------------------------------------------------------
-// ptxas decides per KERNEL, from static instruction counts, whether integer adds, moves and negations go to the ALU
-// pipe (IADD3, MOV) or ride the fma pipe as IMAD.IADD / IMAD.MOV / IMAD.X -- and it counts a wide multiply as one
-// slot, although IMAD.WIDE holds the fma pipe for two.  A kernel whose callers are ALU-heavy (recoding, digit
-// extraction, address arithmetic) therefore gets "passengers" inside the multiplier subroutines: 16 per product in
-// k_verify_ec_vm, 7 % of the pipe that bounds the kernel (profiles/r2_ncu_verify_ec_summary.txt).  The ballast is a
-// block of N plain multiply-adds behind a condition that is never true at run time (never fetched, never executed):
-// it tips the static balance so that the compiler keeps those instructions on the ALU pipe.  `cond` must be opaque to
-// the compiler; the result is stored so the block is not dead code.
-#ifndef BJJ_VM_BALLAST
-#define BJJ_VM_BALLAST 1500
-#endif
-__device__ __forceinline__ void fma_ballast(bool cond, uint32_t seed, uint8_t* sink) {
-#if BJJ_VM_BALLAST > 0
-    if (cond) {
-        uint32_t g = seed, h = seed | 3u;
-#pragma unroll
-        for (int j = 0; j < BJJ_VM_BALLAST; j++) g = g * h + (uint32_t)j;
-        sink[0] = (uint8_t)g;
-    }
-#endif
-}
-
 }  // namespace vm
 }  // namespace bjj
 

@@ -9,6 +9,7 @@ What the constants replace in the reference (paths into /root/reference):
   * Fr Montgomery parameters (ff_ce derive)    Cargo.toml:12, src/lib.rs:7
   * Poseidon round constants / MDS             poseidon-rs 0.0.8 tables behind src/lib.rs:59
 """
+import functools
 import os
 import sys
 
@@ -136,6 +137,7 @@ def _inverse(a):
     return [row[n:] for row in m]
 
 
+@functools.lru_cache(maxsize=None)
 def poseidon_optimized(t):
     rc, mds = poseidon_tables(t)
     rp = R_P[t]
@@ -179,6 +181,73 @@ def poseidon_optimized_eval(inputs):
         what, v = row[2:2 + t - 1], row[2 + t - 1:]
         n0 = (row[1] * x0 + sum(p * q for p, q in zip(what, x[1:]))) % Q
         x = [n0] + [(x[i] + v[i - 1] * x0) % Q for i in range(1, t)]
+    for r in range(R_F // 2, R_F):
+        x = [pow((p + c) % Q, 5, Q) for p, c in zip(x, o["full_rc"][r])]
+        x = _matvec(o["M"], x)
+    return x[0]
+
+
+# ---- grouped partial rounds ---------------------------------------------------------------------
+# In the sparse schedule the lanes 1..t-1 only ACCUMULATE between partial rounds:  x_i <- x_i + v_i * x0.  Over a
+# group of K rounds they are therefore  S_i + sum_m v_(r+m),i * x0_m  with S_i the value at the start of the group, and
+# lane 0 of round r+j is
+#     a_(r+j) * x0_j + sum_(m<j) c_(j,m) * x0_m + sum_i what_(r+j),i * S_i,    c_(j,m) = sum_i what_(r+j),i * v_(r+m),i
+# -- one dot product of t + j terms over values that are already reduced -- and the lanes 1..t-1 are brought up to date
+# once per group by a K-term dot product each.  Per round (t = 6) that is 14.7 limb-products-and-reductions of 64 MACs
+# instead of 17 (K = 3; K = 4 is no better).  Layout of one group of K rounds starting at round r:
+#     for j in 0..K-1:  k_(r+j), a_(r+j), c_(j,j-1), .., c_(j,0), what_(r+j),1..t-1        (t + 1 + j elements)
+#     for i in 1..t-1:  v_(r),i, .., v_(r+K-1),i                                           (K elements)
+# A group of one round is the plain sparse round (k, a00, what, v).
+POSEIDON_GROUP = 3
+# Measured (profiles/r2_ab_poseidon_group.txt): the grouped rounds win for t >= 5 (-8..-10 % time); for t <= 4 the
+# saving is small or negative in MACs (2t + (K-1)/2 + (t-1)/K against 3t - 1 units per round) and the three-round loop
+# body costs more in instruction fetch than it saves, so those widths keep the plain sparse round.
+POSEIDON_GROUP_MIN_T = 5
+
+
+def poseidon_groups(t, group=POSEIDON_GROUP):
+    rows = poseidon_optimized(t)["partial"]
+    rp = len(rows)
+    sizes = [group] * (rp // group) + ([rp % group] if rp % group else [])
+    out, r = [], 0
+    for K in sizes:
+        g = []
+        ks = [rows[r + j][0] for j in range(K)]
+        a = [rows[r + j][1] for j in range(K)]
+        what = [rows[r + j][2:2 + t - 1] for j in range(K)]
+        v = [rows[r + j][2 + t - 1:] for j in range(K)]
+        for j in range(K):
+            c = [sum(w * x for w, x in zip(what[j], v[m])) % Q for m in range(j - 1, -1, -1)]
+            g += [ks[j], a[j]] + c + what[j]
+        for i in range(t - 1):
+            g += [v[m][i] for m in range(K)]
+        assert len(g) == 2 * K * t + K * (K - 1) // 2
+        out.append((K, g))
+        r += K
+    return out
+
+
+def poseidon_grouped_eval(inputs, group=POSEIDON_GROUP):
+    """reference evaluation of the grouped schedule, reading the table exactly as the device does"""
+    t = len(inputs) + 1
+    o = poseidon_optimized(t)
+    x = [0] + [v % Q for v in inputs]
+    for r in range(R_F // 2):
+        x = [pow((p + c) % Q, 5, Q) for p, c in zip(x, o["full_rc"][r])]
+        x = _matvec(o["P"] if r == R_F // 2 - 1 else o["M"], x)
+    x = [(p + c) % Q for p, c in zip(x, o["pre"])]
+    for K, g in poseidon_groups(t, group):
+        x0s, p = [], 0
+        for j in range(K):
+            x0 = pow((x[0] + g[p]) % Q, 5, Q)
+            x0s.append(x0)
+            ops = x0s[::-1] + x[1:]
+            coef = g[p + 1:p + 1 + t + j]
+            x[0] = sum(c * y for c, y in zip(coef, ops)) % Q
+            p += t + 1 + j
+        for i in range(1, t):
+            x[i] = (x[i] + sum(c * y for c, y in zip(g[p:p + K], x0s))) % Q
+            p += K
     for r in range(R_F // 2, R_F):
         x = [pow((p + c) % Q, 5, Q) for p, c in zip(x, o["full_rc"][r])]
         x = _matvec(o["M"], x)
@@ -276,6 +345,9 @@ def emit(out):
         w(" },\n")
     w("};\n\n")
 
+    w("#ifndef BJJ_POSEIDON_GROUP\n#define BJJ_POSEIDON_GROUP %d\n#endif\n" % POSEIDON_GROUP)
+    w("#if BJJ_POSEIDON_GROUP != 1 && BJJ_POSEIDON_GROUP != %d\n#error \"the tables are generated for groups of 1 or %d partial rounds\"\n#endif\n\n"
+      % (POSEIDON_GROUP, POSEIDON_GROUP))
     for t in range(2, 8):        # poseidon-rs 0.0.8 accepts 1..6 inputs
         o = poseidon_optimized(t)
         w("#define BJJ_POSEIDON_RP_%d %d\n" % (t, R_P[t]))
@@ -288,8 +360,14 @@ def emit(out):
             w("};\n")
         table("FC", [c for r in o["full_rc"] for c in r], "round constants of the 8 full rounds, [round][lane]")
         table("PRE", o["pre"], "vector added once before the partial rounds")
+        w("#define BJJ_POSEIDON_GROUP_%d %s\n" % (t, "BJJ_POSEIDON_GROUP" if t >= POSEIDON_GROUP_MIN_T else "1"))
+        w("#if BJJ_POSEIDON_GROUP_%d == 1\n" % t)
         table("PR", [e for r in o["partial"] for e in r],
               "per partial round: k, a00, what[1..t-1], v[1..t-1]  (2t elements)")
+        w("#else\n")
+        table("PR", [e for _, g in poseidon_groups(t) for e in g],
+              "partial rounds in groups of %d (+ one shorter group): see gen_constants.py::poseidon_groups" % POSEIDON_GROUP)
+        w("#endif\n")
         table("M", [o["M"][i][j] for i in range(t) for j in range(t)], "row-major MDS")
         table("P", [o["P"][i][j] for i in range(t) for j in range(t)], "row-major matrix of full round 3 (= A'_1 * M)")
         w("\n")

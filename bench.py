@@ -47,28 +47,50 @@ METRIC = "eddsa_poseidon_verifies_per_sec"
 UNIT = "verifies/s"
 
 # Algorithmic work per unit, in limb-MACs (one 32x32->64 multiply-accumulate = one IMAD.WIDE.U32 on sm_100a).
-# fmul = fsqr = 128 (8x8 products + 8x8 Montgomery reduction; the 8 m_i IMADs are not counted), a Montgomery dot
-# product of N terms = 64 N + 64.  Counts are for the algorithms actually built; derivations in DESIGN.md section 6.
+# fmul = 128 (8x8 products + 8x8 Montgomery reduction), fsqr = 100 (36 products of the squaring triangle + the same
+# reduction), a Montgomery dot product of N terms = 64 N + 64.  Counts are for the algorithms actually built, as
+# (multiplications, squarings); derivations in DESIGN.md section 6.
 FMUL = 128
-ALGO_FMUL = {
-    # k_verify_hash besides Poseidon: two on-curve gates 10 + Montgomery conversions 6
-    "verify_hash_extra": 10 + 6,
-    # k_verify_ec (half-size scalars, 33 radix-16 windows over the tables of 8A and R8):
-    # conversions 4 + map 4 + 8A 22 + two 9-entry tables 2 x 64 + 32 x (3 x 7 + 8) doublings
+FSQR = 100
+
+
+def mac(mul, sqr=0):
+    return mul * FMUL + sqr * FSQR
+
+
+FERMAT = (126, 254)                                    # fr_inv: a^(Q-2), plain binary: 254 squarings, 126 multiplications
+ALGO_OPS = {
+    # k_verify_hash besides Poseidon: two on-curve gates (2 squarings + 3 multiplications each) + 6 Montgomery conversions
+    "verify_hash_extra": (6 + 6, 4),
+    # k_verify_ec_vm (half-size scalars, 33 radix-16 windows over the tables of 8A and R8): conversions 4 + map 4
+    # + 8A = 3 doublings (4S + 3M, 4S + 4M for the last) + two 9-entry tables 2 x 64 + 32 x 4 doublings
     # + 33 x (8 + 7) table additions + 1 + 17 B8 additions (16 x 7 + 6)
-    "verify_ec": 4 + 4 + 22 + 128 + 32 * 29 + 33 * 15 + 1 + 16 * 7 + 6,
-    "fixed_base": 17 * 7 + 1 + 5 + 2 + 12,            # 16-bit comb + map + batched inversion share
-    "mul_scalar": 2 + 5 + 2 + 64 + 7 + 64 * 36 + 20,  # gate, table, 64 windows x (4 dbl + add), batched inversion share
+    "verify_ec": (4 + 4 + 10 + 128 + 32 * 13 + 33 * 15 + 1 + 16 * 7 + 6, 12 + 32 * 16),
+    # 16-bit comb (17 mixed additions) + map + batched inversion: 5 per lane + one Fermat inversion per 32 lanes
+    "fixed_base": (17 * 7 + 1 + 5 + 2 + FERMAT[0] / 32, FERMAT[1] / 32),
+    # gate (2S + 3M), conversions, 9-entry table, 64 windows x (4 doublings + 1 addition), batched inversion share
+    "mul_scalar": (3 + 4 + 2 + 64 + 7 + 64 * (13 + 7) + 5 + FERMAT[0] / 32, 2 + 64 * 16 + FERMAT[1] / 32),
+    # decompress_point: y^2, d y^2; batched inversion (3 + Fermat / 32); x^2 = u / v; a^((T-1)/2) plain binary over a
+    # 225-bit exponent of weight 99; x0, b; Pohlig-Hellman 21 + 14 + 7 squarings and 8 multiplications; x0^2; 3 conversions
+    "decompress": (1 + 3 + FERMAT[0] / 32 + 1 + 99 + 2 + 8 + 3, 1 + FERMAT[1] / 32 + 225 + 42 + 1),
+    # PointProjective::add, literal add-2008-bbjlp as src/lib.rs:88-131 sequences it (12 multiplications + 1 squaring) + 9 conversions
+    "proj_add": (12 + 9, 1),
 }
-# Poseidon t = 6, sparse schedule: 8 full rounds x (6 x^5 + 6 dot6) + 60 partial x (x^5 + dot6 + 5 fmul)
-POSEIDON6_MAC = 8 * (6 * 3 * FMUL + 6 * (6 * 64 + 64)) + 60 * (3 * FMUL + (6 * 64 + 64) + 5 * FMUL)
+
+
+def poseidon_mac(t, rounds_p, n_inputs):
+    """sparse schedule: 8 full rounds x (t S-boxes x^5 = 2S + 1M, t dot products of t terms) + R_P partial rounds x
+    (one S-box, one dot product, t - 1 multiplications) + the Montgomery conversions of the inputs and the output"""
+    sbox = mac(1, 2)
+    dot = t * 64 + 64
+    return 8 * (t * sbox + t * dot) + rounds_p * (sbox + dot + mac(t - 1)) + mac(n_inputs + 1)
+
+
+POSEIDON6_MAC = poseidon_mac(6, 60, 0)
 # k_verify_split: ~75 Euclid steps x (8 + 8) wide multiplies + two Montgomery products mod l
 SPLIT_MAC = 75 * 16 + 2 * FMUL
-ALGO_MAC = {
-    "verify": (ALGO_FMUL["verify_hash_extra"] + ALGO_FMUL["verify_ec"]) * FMUL + POSEIDON6_MAC + SPLIT_MAC,
-    "fixed_base": ALGO_FMUL["fixed_base"] * FMUL,
-    "mul_scalar": ALGO_FMUL["mul_scalar"] * FMUL,
-}
+ALGO_MAC = {k: mac(*v) for k, v in ALGO_OPS.items()}
+ALGO_MAC["verify"] = ALGO_MAC["verify_hash_extra"] + ALGO_MAC["verify_ec"] + POSEIDON6_MAC + SPLIT_MAC
 # Measured on B200 (profiles/r1_pipe_probe.jsonl): IMAD.WIDE.U32 issues at 32 lanes/clk/SM -- half the 32-bit IMAD
 # rate that SURVEY.md section 8d's model (64 lanes/clk/SM) assumes.
 WIDE_MAC_LANES_PER_CLK_SM = 32
@@ -576,7 +598,7 @@ def run_ours(args, rank, local_rank, world):
                         "workload": "verify_compressed_batch: 2^%d x (64 B sig + 32 B pk + 32 B msg) in all, 2^%d/%d per GPU; decompress R8 and A -> "
                                     "Poseidon -> Straus" % (args.log2_total, args.log2_total, world),
                         "value": rate, "unit": "verifies/s", "n_gpus": world, "scaling": "strong", "ms_per_step": ms,
-                        "roofline_frac_imad": rate / world * (ALGO_MAC["verify"] + 2 * 345 * FMUL) / imad_peak, "oracle_checked_lanes": 2048})
+                        "roofline_frac_imad": rate / world * (ALGO_MAC["verify"] + 2 * ALGO_MAC["decompress"]) / imad_peak, "oracle_checked_lanes": 2048})
         del sig64, comp_a, m5, ok5, st5
         torch.cuda.empty_cache()
 
@@ -734,7 +756,7 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
     lib.bjj_compress_batch_dev(ctx, n, dptr(ax[:n]), dptr(ay[:n]), dptr(comp_a), sp)
     lib.bjj_compress_batch_dev(ctx, n, dptr(r8x[:n]), dptr(r8y[:n]), dptr(comp_r), sp)
 
-    # decompress_point (row a7): 2^20 compressed points, ~345 fmul each -> IMAD-bound
+    # decompress_point (row a7): 2^20 compressed points, ~125 multiplications + ~275 squarings each -> IMAD-bound
     st2 = torch.empty(n, dtype=torch.uint8, device=dev)
     dx, dy = (torch.empty((n, 32), dtype=torch.uint8, device=dev) for _ in range(2))
     ms = timed(lambda: lib.bjj_decompress_batch_dev(ctx, n, dptr(comp_r), dptr(dx), dptr(dy), dptr(st2), sp), args.steps)
@@ -742,7 +764,7 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
     assert np.array_equal(dx[:1024].cpu().numpy(), ex) and np.array_equal(st2[:1024].cpu().numpy(), est), "decompress_batch parity"
     rate = n / (ms * 1e-3)
     out.append({"metric": "decompress_points_per_sec", "workload": "decompress_batch: 2^20 compressed points", "value": rate,
-                "unit": "points/s", "ms_per_step": ms, "roofline_frac_imad": rate * 345 * FMUL / imad_peak, "oracle_checked_lanes": 1024})
+                "unit": "points/s", "ms_per_step": ms, "roofline_frac_imad": rate * ALGO_MAC["decompress"] / imad_peak, "oracle_checked_lanes": 1024})
 
     # POSEIDON.hash, every width poseidon-rs accepts (row a8 + next row f-2): t = n_inputs + 1
     rounds_p = [56, 57, 56, 60, 60, 63]                  # poseidon-rs / circomlib R_P for t = 2..7 (R_F = 8)
@@ -756,14 +778,14 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
         assert np.array_equal(ho[:128].cpu().numpy(), eh), "poseidon_batch parity (t = %d)" % (nin + 1)
         t = nin + 1
         rp = rounds_p[t - 2]
-        mac = 8 * (t * 3 * FMUL + t * (t * 64 + 64)) + rp * (3 * FMUL + (t * 64 + 64) + (t - 1) * FMUL) + (nin + 1) * FMUL
+        pmac = poseidon_mac(t, rp, nin)
         rate = n / (ms * 1e-3)
         out.append({"metric": "poseidon%d_hashes_per_sec" % nin, "workload": "poseidon_batch: 2^20 x %d inputs (t = %d)" % (nin, t),
                     "value": rate, "unit": "hashes/s", "ms_per_step": ms,
-                    "roofline_frac_imad": rate * mac / imad_peak, "oracle_checked_lanes": 128})
+                    "roofline_frac_imad": rate * pmac / imad_peak, "oracle_checked_lanes": 128})
 
     # PrivateKey::sign (next row f-3): BLAKE-512 x2, two fixed-base multiplications (2 x 17 x 7 fmul), ONE shared
-    # inversion for the two affine conversions (~390 fmul), Poseidon, S
+    # Fermat inversion for the two affine conversions, Poseidon, S
     ns = 1 << 19
     o = [torch.empty((ns, 32), dtype=torch.uint8, device=dev) for _ in range(3)]
     sst = torch.empty(ns, dtype=torch.uint8, device=dev)
@@ -773,7 +795,7 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
     assert all(np.array_equal(o[k][:256].cpu().numpy(), er[k]) for k in range(3)), "sign_batch parity"
     rate = ns / (ms * 1e-3)
     out.append({"metric": "signatures_per_sec", "workload": "sign_batch: 2^19 (key, msg) pairs", "value": rate, "unit": "signatures/s",
-                "ms_per_step": ms, "roofline_frac_imad": rate * ((2 * 17 * 7 + 12 + 390) * FMUL + POSEIDON6_MAC) / imad_peak,
+                "ms_per_step": ms, "roofline_frac_imad": rate * (mac(2 * 17 * 7 + 12 + 10 + FERMAT[0], FERMAT[1]) + POSEIDON6_MAC) / imad_peak,
                 "oracle_checked_lanes": 256})
 
     # verify_schnorr (next row f-4): the verify pipeline with full-width scalars (64-65 windows)
@@ -797,7 +819,7 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
     assert np.array_equal(oka[:256].cpu().numpy(), eok), "adversarial verify parity"
     out.append({"metric": "adversarial_verifies_per_sec", "workload": "verify_batch: 2^17 signatures, 100% off-curve A (every lane replays "
                 "the reference's LSB-first double-and-add literally)", "value": na / (ms * 1e-3), "unit": "verifies/s", "ms_per_step": ms,
-                "roofline_frac_imad": na / (ms * 1e-3) * (257 * 26 + 17 * 7 + 400 + 1000) * FMUL / imad_peak, "oracle_checked_lanes": 256})
+                "roofline_frac_imad": na / (ms * 1e-3) * (mac(257 * 24 + 17 * 7 + 20 + FERMAT[0], 257 * 2 + FERMAT[1]) + POSEIDON6_MAC) / imad_peak, "oracle_checked_lanes": 256})
 
     # Point::compress (row a6): pure data movement, 64 B in + 32 B out per point -> HBM-bound
     n = 1 << 22
@@ -826,7 +848,7 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
     assert all(np.array_equal(o3[k][:1024].cpu().numpy(), ea[k]) for k in range(3)), "add_batch parity"
     rate = n / (ms * 1e-3)
     out.append({"metric": "projective_adds_per_sec", "workload": "add_batch: 2^21 projective pairs (literal add-2008-bbjlp)",
-                "value": rate, "unit": "adds/s", "ms_per_step": ms, "roofline_frac_imad": rate * 22 * FMUL / imad_peak,
+                "value": rate, "unit": "adds/s", "ms_per_step": ms, "roofline_frac_imad": rate * ALGO_MAC["proj_add"] / imad_peak,
                 "hbm_frac": rate * 288 / 1e9 / hbm_peak, "oracle_checked_lanes": 1024})
     return out
 

@@ -55,3 +55,20 @@ def test_optimized_poseidon_schedule_equals_dense():
     for t in range(2, 8):
         for ins in ([0] * (t - 1), list(range(1, t)), [rnd.randrange(Q) for _ in range(t - 1)]):
             assert g.poseidon_optimized_eval(ins) == O.poseidon(ins), t
+
+
+def test_grouped_poseidon_schedule_equals_dense():
+    """the grouped partial rounds (three rounds share the reductions of lanes 1..t-1; gen_constants.py::poseidon_groups),
+    evaluated from the table the device reads, must hash like the dense oracle -- for every group size"""
+    import random
+    g = _gen()
+    rnd = random.Random(10)
+    for t in range(2, 8):
+        for ins in ([0] * (t - 1), [Q - 1] * (t - 1), [rnd.randrange(Q) for _ in range(t - 1)]):
+            want = O.poseidon(ins)
+            for group in (1, 2, 3, 4):
+                assert g.poseidon_grouped_eval(ins, group) == want, (t, group)
+    # table geometry the device code assumes
+    for t in range(2, 8):
+        for K, row in g.poseidon_groups(t):
+            assert len(row) == 2 * K * t + K * (K - 1) // 2
