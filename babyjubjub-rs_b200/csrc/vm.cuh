@@ -101,18 +101,6 @@ static __device__ __noinline__ void sqr2(Slot d0, Slot a0, Slot d1, Slot a1) {
     st(d0, r0);
     st(d1, r1);
 }
-// the same with the second factors read from global memory (window-table / comb entries)
-static __device__ __noinline__ void mul2_g(Slot d0, Slot a0, const uint4* g0, Slot d1, Slot a1, const uint4* g1, size_t hstride) {
-    Fr x0, y0, x1, y1, r0, r1;
-    ldg(y0, g0, hstride);
-    ldg(y1, g1, hstride);
-    ld(x0, a0);
-    ld(x1, a1);
-    fr_mul_inline(r0, x0, y0);
-    fr_mul_inline(r1, x1, y1);
-    st(d0, r0);
-    st(d1, r1);
-}
 // d = a + b, d = a - b (lazy domain [0, 2Q))
 static __device__ __noinline__ void add(Slot d, Slot a, Slot b) {
     Fr x, y, r;

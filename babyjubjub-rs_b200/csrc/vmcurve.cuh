@@ -30,14 +30,6 @@ static __device__ __noinline__ void mul_c(Slot d, Slot a, int which) {
     fr_mul_inline(r, c, x);
     st(d, r);
 }
-// d = a * [g]
-static __device__ __noinline__ void mul_g(Slot d, Slot a, const uint4* g, size_t hstride) {
-    Fr x, y, r;
-    ldg(y, g, hstride);
-    ld(x, a);
-    fr_mul_inline(r, x, y);
-    st(d, r);
-}
 static __device__ __noinline__ void neg(Slot d, Slot a) {
     Fr x, r;
     ld(x, a);
@@ -111,15 +103,30 @@ __device__ __forceinline__ void dbl(const Regs& s, bool want_t) {
 // acc += (-1)^negate * entry, the entry in GLOBAL memory as (y+x, y-x, 2d'T[, 2Z]): coordinate c at e + c * cstride,
 // halves `hstride` apart.  affine: Z(entry) = 1, the fourth coordinate is not read.  (curve.cuh::ext_add_niels[_aff];
 // the negation swaps the first two coordinates and the roles of F and G instead of negating 2d'T.)
+// The entry's coordinates travel global -> caller registers -> free slots: the loads are issued one subroutine call
+// ahead of their use (their L2/HBM latency runs under ~70 or ~1,000 instructions of arithmetic), and the products then
+// go through the SAME mul2/mul as everything else.  A mul2 variant with its second factors in global memory was the
+// first design; with the squaring subroutine added it pushed the hot code of the Straus loop from 23 to 29 KB, past
+// the instruction cache, and the kernel fell to 79 % multiplier-pipe activity with 1.9 `no_instruction` stalls per
+// issue (profiles/r2_ncu_verify_ec_summary.txt).
 __device__ __forceinline__ void add_entry(const Regs& s, const uint4* e, size_t cstride, size_t hstride, bool negate, bool affine,
                                           bool want_t) {
+    Fr g0, g1;
+    ldg(g0, e + (negate ? cstride : 0), hstride);
+    ldg(g1, e + (negate ? 0 : cstride), hstride);
     addsub(s.t0, s.t1, s.Y, s.X);                                                                   // Y+X, Y-X
-    mul2_g(s.t0, s.t0, e + (negate ? cstride : 0), s.t1, s.t1, e + (negate ? 0 : cstride), hstride);  // A, B
+    st(s.t2, g0);
+    st(s.t3, g1);
+    ldg(g0, e + 2 * cstride, hstride);
+    if (!affine) ldg(g1, e + 3 * cstride, hstride);
+    mul2(s.t0, s.t0, s.t2, s.t1, s.t1, s.t3);                                                       // A, B
+    st(s.t2, g0);
     if (affine) {
-        mul_g(s.t2, s.T, e + 2 * cstride, hstride);                                                 // C
+        mul(s.t2, s.T, s.t2);                                                                       // C
         add(s.t3, s.Z, s.Z);                                                                        // D = 2Z
     } else {
-        mul2_g(s.t2, s.T, e + 2 * cstride, s.t3, s.Z, e + 3 * cstride, hstride);                    // C, D
+        st(s.t4, g1);
+        mul2(s.t2, s.T, s.t2, s.t3, s.Z, s.t4);                                                     // C, D
     }
     addsub(s.t4, s.t0, s.t0, s.t1);                                                                 // H = A + B, E = A - B
     addsub(negate ? s.t2 : s.t1, negate ? s.t1 : s.t2, s.t3, s.t2);                                 // G -> t1, F -> t2

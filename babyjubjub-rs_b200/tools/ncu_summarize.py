@@ -33,16 +33,10 @@ RAW = [
     "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
 ]
 FMA_LIGHT = ("IMAD.MOV", "IMAD.IADD", "IMAD.X", "IMAD.SHL", "IMAD", "HFMA2", "IMAD.HI", "FFMA", "FMUL", "FADD")
-# algorithmic IMAD.WIDE per lane (128 per field multiplication), by kernel-name prefix
-ALGO_WIDE_PER_LANE = {
-    "k_verify_ec_vm": (4 + 4 + 22 + 128 + 32 * 29 + 33 * 15 + 1 + 16 * 7 + 6) * 128,
-    "k_verify_hash": 16 * 128 + 8 * (18 * 128 + 6 * 448) + 60 * (3 * 128 + 448 + 5 * 128) + 128,
-    "k_poseidon": 6 * 128 + 8 * (18 * 128 + 6 * 448) + 60 * (3 * 128 + 448 + 5 * 128),
-    "k_fixed_base": (17 * 7 + 1) * 128,
-    "k_public": (17 * 7 + 1) * 128,
-    "k_mul_scalar(": (2 + 5 + 2 + 64 + 7 + 64 * 36) * 128,
-    "k_decompress_finish": 335 * 128,
-}
+# algorithmic IMAD.WIDE per lane by kernel-name prefix: bench.py::KERNEL_MAC (fmul = 128, fsqr = 100)
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from bench import KERNEL_MAC as ALGO_WIDE_PER_LANE  # noqa: E402
 TO_BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TO_MS = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3, "nsecond": 1e-6}
 
@@ -131,7 +125,7 @@ def main():
             txt.append("  top opcodes: " + ", ".join("%s %d" % kv for kv in ex.most_common(10)))
         algo = None
         for pfx, v in ALGO_WIDE_PER_LANE.items():
-            if name.startswith(pfx) or (pfx.endswith("(") and name.startswith(pfx)):
+            if pfx in name:
                 algo = v
         out = {
             "ms_per_2p20_lanes": m.get("ms"),

@@ -79,11 +79,25 @@ ALGO_OPS = {
 
 
 def poseidon_mac(t, rounds_p, n_inputs):
-    """sparse schedule: 8 full rounds x (t S-boxes x^5 = 2S + 1M, t dot products of t terms) + R_P partial rounds x
-    (one S-box, one dot product, t - 1 multiplications) + the Montgomery conversions of the inputs and the output"""
+    """the schedule of csrc/poseidon.cuh: 7 full rounds x (t S-boxes x^5 = 2S + 1M, t dot products of t terms) + the
+    last full round (t S-boxes, ONE dot product); partial rounds: t <= 4 one S-box, one dot product, t - 1
+    multiplications per round; t >= 5 in groups of three rounds (dot products of t, t + 1, t + 2 terms, then t - 1 dot
+    products of 3 terms); + the Montgomery conversions of the inputs and the output"""
     sbox = mac(1, 2)
-    dot = t * 64 + 64
-    return 8 * (t * sbox + t * dot) + rounds_p * (sbox + dot + mac(t - 1)) + mac(n_inputs + 1)
+
+    def dot(n):
+        return n * 64 + 64
+    full = 7 * (t * sbox + t * dot(t)) + t * sbox + dot(t)
+    if t >= 5:
+        groups, rem = divmod(rounds_p, 3)
+        partial = groups * (3 * sbox + dot(t) + dot(t + 1) + dot(t + 2) + (t - 1) * dot(3))
+        if rem == 2:
+            partial += 2 * sbox + dot(t) + dot(t + 1) + (t - 1) * dot(2)
+        elif rem == 1:
+            partial += sbox + dot(t) + mac(t - 1)
+    else:
+        partial = rounds_p * (sbox + dot(t) + mac(t - 1))
+    return full + partial + mac(n_inputs + 1)
 
 
 POSEIDON6_MAC = poseidon_mac(6, 60, 0)
@@ -91,6 +105,16 @@ POSEIDON6_MAC = poseidon_mac(6, 60, 0)
 SPLIT_MAC = 75 * 16 + 2 * FMUL
 ALGO_MAC = {k: mac(*v) for k, v in ALGO_OPS.items()}
 ALGO_MAC["verify"] = ALGO_MAC["verify_hash_extra"] + ALGO_MAC["verify_ec"] + POSEIDON6_MAC + SPLIT_MAC
+# the same counts per KERNEL launch and lane (tools/ncu_summarize.py divides the executed IMAD.WIDE of a capture by these)
+KERNEL_MAC = {
+    "k_verify_ec_vm": ALGO_MAC["verify_ec"],
+    "k_verify_hash": ALGO_MAC["verify_hash_extra"] + POSEIDON6_MAC,
+    "k_poseidon<6>": poseidon_mac(6, 60, 5),
+    "k_fixed_base": mac(17 * 7 + 3),
+    "k_public": mac(17 * 7 + 3),
+    "k_mul_scalar(": mac(3 + 4 + 2 + 64 + 7 + 64 * 20 + 2, 2 + 64 * 16),
+    "k_decompress_finish": mac(1 + 1 + 99 + 2 + 8 + 2, 225 + 42 + 1),
+}
 # Measured on B200 (profiles/r1_pipe_probe.jsonl): IMAD.WIDE.U32 issues at 32 lanes/clk/SM -- half the 32-bit IMAD
 # rate that SURVEY.md section 8d's model (64 lanes/clk/SM) assumes.
 WIDE_MAC_LANES_PER_CLK_SM = 32
