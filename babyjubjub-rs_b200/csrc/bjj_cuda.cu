@@ -60,17 +60,28 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_batch_affine(size_t n, ProjScratc
     batch_affine_strided(scr, rx, ry, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
+// The point kernels claim their lanes dynamically (BJJ_CLAIM_LOOP), like the verify kernels: with a static grid-stride
+// split the kernel lasts as long as its slowest CTA and ncu showed 80 % (k_fixed_base, k_public) and 68 %
+// (k_decompress_finish) of the resident warps active on average.  BJJ_POINT_CLAIM=0 restores the static split.
+#ifndef BJJ_POINT_CLAIM
+#define BJJ_POINT_CLAIM 1
+#endif
+#if BJJ_POINT_CLAIM
+#define BJJ_POINT_LOOP(n, work) BJJ_CLAIM_LOOP(n, work) if (i < (n))
+#else
+#define BJJ_POINT_LOOP(n, work) BJJ_LANE_LOOP(n)
+#endif
 __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_fixed_base(size_t n, const uint8_t* k, ProjScratch scr,
-                                                          const CombEntry* comb) {
-    BJJ_LANE_LOOP(n) lane_fixed_base(k, scr, i, comb);
+                                                          const CombEntry* comb, unsigned long long* work) {
+    BJJ_POINT_LOOP(n, work) lane_fixed_base(k, scr, i, comb);
 }
 
 #ifndef BJJ_PUBLIC_BALLAST
 #define BJJ_PUBLIC_BALLAST 1
 #endif
 __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_public(size_t n, const uint8_t* key, ProjScratch scr,
-                                                      const CombEntry* comb) {
-    BJJ_LANE_LOOP(n) lane_public(key, scr, i, comb);
+                                                      const CombEntry* comb, unsigned long long* work) {
+    BJJ_POINT_LOOP(n, work) lane_public(key, scr, i, comb);
 #if BJJ_PUBLIC_BALLAST
     fma_ballast(comb == nullptr, (uint32_t)n, scr.y);      // never taken (fr.cuh): BLAKE-512 makes this kernel ALU-heavy
 #endif
@@ -99,8 +110,8 @@ __global__ void __launch_bounds__(BJJ_BLOCK) k_batch_inverse(size_t n, ProjScrat
 }
 __global__ void __launch_bounds__(BJJ_BLOCK, 2) k_decompress_finish(size_t n, const uint8_t* in, size_t stride, size_t off,
                                                                  ProjScratch scr, size_t slot0, uint8_t* rx, uint8_t* ry,
-                                                                 uint8_t* status, int merge) {
-    BJJ_LANE_LOOP(n) lane_decompress_finish(in, stride, off, scr, slot0 + i, rx, ry, status, i, merge != 0);
+                                                                 uint8_t* status, int merge, unsigned long long* work) {
+    BJJ_POINT_LOOP(n, work) lane_decompress_finish(in, stride, off, scr, slot0 + i, rx, ry, status, i, merge != 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -119,6 +130,8 @@ struct Workspace {
     size_t vs_lanes;
     uint8_t* kred;           // wide scalars reduced mod ORDER (32 B per lane)
     size_t kred_lanes;
+    unsigned long long* claim;      // BJJ_CLAIM_SLOTS lane-claim counters of the point kernels, handed out round-robin
+    unsigned claim_next;
     cudaStream_t aux;        // side stream: the exact-lane kernel overlaps the fast EC kernel
     cudaEvent_t ev_fork, ev_join;
 };
@@ -212,6 +225,17 @@ static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, 
     return BJJ_OK;
 }
 
+// A zeroed lane-claim counter for ONE launch on `st` (kernels.h::BJJ_CLAIM_LOOP).  Slots rotate, so that the memset of
+// the next launch never touches the counter of a launch that is still running on the same stream order.
+#define BJJ_CLAIM_SLOTS 16
+static int claim_counter(bjj_ctx* ctx, Workspace* ws, cudaStream_t st, unsigned long long** out) {
+    if (!ws->claim) CU(ctx, cudaMalloc(&ws->claim, BJJ_CLAIM_SLOTS * sizeof(unsigned long long)));
+    unsigned long long* c = ws->claim + (ws->claim_next++ % BJJ_CLAIM_SLOTS);
+    CU(ctx, cudaMemsetAsync(c, 0, sizeof(unsigned long long), st));
+    *out = c;
+    return BJJ_OK;
+}
+
 static unsigned long long* work_counters(Workspace* ws) { return reinterpret_cast<unsigned long long*>(ws->exact_count + 4); }
 
 // sub-batch size of the point kernels: bounds the projective scratch at 4 x 32 B x 2^21 = 256 MiB
@@ -262,6 +286,7 @@ static void free_workspace(Workspace* ws) {
     if (ws->vs) cudaFree(ws->vs);
     if (ws->kred) cudaFree(ws->kred);
     if (ws->exact_count) cudaFree(ws->exact_count);
+    if (ws->claim) cudaFree(ws->claim);
     if (ws->exact_list) cudaFree(ws->exact_list);
     memset(ws, 0, sizeof(*ws));
 }
@@ -484,10 +509,13 @@ static int launch_fixed_base(bjj_ctx* ctx, size_t n, const uint8_t* in, uint8_t*
         ProjScratch scr;
         int rc = ensure_proj(ctx, ws, m < BJJ_POINT_SUBBATCH && n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &scr);
         if (rc) return rc;
+        unsigned long long* work = nullptr;
+        rc = claim_counter(ctx, ws, st, &work);
+        if (rc) return rc;
         if (from_keys)
-            k_public<<<grid_for(ctx, (const void*)k_public, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb);
+            k_public<<<grid_for(ctx, (const void*)k_public, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb, work);
         else
-            k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb);
+            k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb, work);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         k_batch_affine<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr, rx + o, ry + o);
@@ -510,8 +538,11 @@ static int launch_decompress(bjj_ctx* ctx, size_t n, const uint8_t* in32, uint8_
         k_batch_inverse<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
+        unsigned long long* work = nullptr;
+        rc = claim_counter(ctx, ws, st, &work);
+        if (rc) return rc;
         k_decompress_finish<<<grid_for(ctx, (const void*)k_decompress_finish, m), BJJ_BLOCK, 0, st>>>(m, in32 + o, 1, 0, scr, 0, rx + o,
-                                                                                                     ry + o, status + off, 0);
+                                                                                                     ry + o, status + off, 0, work);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
     }
@@ -636,8 +667,13 @@ static int launch_verify_compressed(bjj_ctx* ctx, size_t n, const uint8_t* sig64
         k_decompress_prepare<<<grid_p, BJJ_BLOCK, 0, st>>>(m, sig64 + 2 * o, 2, 0, scr, 0);
         k_decompress_prepare<<<grid_p, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m);
         k_batch_inverse<<<affine_grid(ctx, 2 * m), BJJ_BLOCK, 0, st>>>(2 * m, scr);
-        k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, sig64 + 2 * o, 2, 0, scr, 0, dx, dy, status + off, 0);
-        k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m, dax, day, status + off, 1);
+        unsigned long long *work_r = nullptr, *work_a = nullptr;
+        rc = claim_counter(ctx, ws, st, &work_r);
+        if (rc) return rc;
+        rc = claim_counter(ctx, ws, st, &work_a);
+        if (rc) return rc;
+        k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, sig64 + 2 * o, 2, 0, scr, 0, dx, dy, status + off, 0, work_r);
+        k_decompress_finish<<<grid_f, BJJ_BLOCK, 0, st>>>(m, pk32 + o, 1, 0, scr, m, dax, day, status + off, 1, work_a);
         ctx->launches += 5;
         CU(ctx, cudaGetLastError());
         bjjk::verify_hash(grid_h, st, m, dx, dy, dax, day, msg + o, sig64 + 2 * o, 2, 1, status + off, hm, ws->vs_lanes, ok + off, false, q,

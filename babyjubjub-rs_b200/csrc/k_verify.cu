@@ -53,6 +53,9 @@ __global__ void __launch_bounds__(BJJ_BLOCK, 4) k_verify_split(size_t n, const u
 #define BJJ_EC_VM_MINB 5
 #endif
 #define BJJ_EC_VM_SLOTS (BJJ_VM_REG_SLOTS + 2)
+#ifndef BJJ_EC_PREFETCH
+#define BJJ_EC_PREFETCH 1
+#endif
 
 __device__ __forceinline__ int vm_digit4(vm::Slot s, uint32_t top, int i) {      // signed radix-16 digit i in [0, 64]
     const uint32_t w = vm::ld_word(s, (i >> 3) & 7);
@@ -110,12 +113,19 @@ __device__ __forceinline__ void lane_verify_ec_vm(const uint8_t* r8x, const uint
     set_identity(s);
 #pragma unroll 1
     for (int k = nwin - 1; k >= 0; k--) {
+        // the two table entries of this window are requested into L2 before the doublings: the window tables (218 MB
+        // per workspace) do not stay in L2, and a load is waited for at the next subroutine call
+        const int da = vm_digit4(su, tops & 1u, k), dr = vm_digit4(sv, tops >> 1, k);
+#if BJJ_EC_PREFETCH
+        prefetch_l2(ta.entry(da < 0 ? -da : da));
+        prefetch_l2(tr.entry(dr < 0 ? -dr : dr));
+#endif
         if (k != nwin - 1) {
 #pragma unroll 1
             for (int j = 0; j < 4; j++) dbl(s, j == 3);
         }
-        add_digit(s, ta, vm_digit4(su, tops & 1u, k), true);
-        add_digit(s, tr, vm_digit4(sv, tops >> 1, k), k == 0);       // T only where the B8 additions follow
+        add_digit(s, ta, da, true);
+        add_digit(s, tr, dr, k == 0);       // T only where the B8 additions follow
     }
     // + w * B8: 16 signed 16-bit digits and the recoding carry against the fixed-base table, no doubling
     {

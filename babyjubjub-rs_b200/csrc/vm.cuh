@@ -60,6 +60,9 @@ __device__ __forceinline__ void stg(uint4* p, size_t hstride, const Fr& r) {
     p[hstride] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+// request the 128-byte line at p into L2 (no register, no scoreboard: nothing waits for it)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- the out-of-line operations --------------------------------------------------------------------
 // (One multiplication per call through a single ~3 KB subroutine was measured too: 63.2 ms against 60.5 ms for the
 // pairs below in the Straus kernel -- the second carry chain in flight is worth more than the smaller footprint.)
