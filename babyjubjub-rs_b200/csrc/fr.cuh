@@ -519,8 +519,39 @@ BJJ_HD void fr_pow(Fr& r, const Fr& a, const uint32_t* e, int nbits) {
     r = acc;
 }
 
-// Fermat inverse; 0 -> 0.
-BJJ_HD void fr_inv(Fr& r, const Fr& a) { fr_pow(r, a, BJJ_EXP_QM2, 254); }
+// r = a^e for one of the library's two fixed exponents, by the sliding-window schedule generated at build time
+// (tools/gen_constants.py::pow_schedule: window of 4 bits over the odd powers a, a^3, .., a^15).  The schedule is the
+// same for every lane, so the walk does not diverge; the table of odd powers is indexed dynamically and lives in local
+// memory (256 B per thread, read once per step).  One squaring body and one multiplication body in the instruction stream.
+BJJ_HD void fr_pow_sched(Fr& r, const Fr& a, const uint8_t (*steps)[2], int nsteps, int tail) {
+    Fr tab[BJJ_POW_TABLE], a2;
+    tab[0] = a;
+    fr_sqr(a2, a);
+#pragma unroll 1
+    for (int i = 1; i < BJJ_POW_TABLE; i++) fr_mul(tab[i], tab[i - 1], a2);
+    Fr acc = tab[steps[0][1]];
+#pragma unroll 1
+    for (int k = 1; k < nsteps; k++) {
+#pragma unroll 1
+        for (int s = steps[k][0]; s > 0; s--) fr_sqr(acc, acc);
+        fr_mul(acc, acc, tab[steps[k][1]]);
+    }
+#pragma unroll 1
+    for (int s = tail; s > 0; s--) fr_sqr(acc, acc);
+    r = acc;
+}
+
+// Fermat inverse a^(Q-2); 0 -> 0.  (BJJ_POW_SCHED=0: plain binary exponentiation, 254 squarings + 126 multiplications.)
+#ifndef BJJ_POW_SCHED
+#define BJJ_POW_SCHED 1
+#endif
+BJJ_HD void fr_inv(Fr& r, const Fr& a) {
+#if BJJ_POW_SCHED
+    fr_pow_sched(r, a, BJJ_POW_QM2, BJJ_POW_QM2_STEPS, BJJ_POW_QM2_TAIL);
+#else
+    fr_pow(r, a, BJJ_EXP_QM2, 254);
+#endif
+}
 
 // ---- pipe-selection ballast ----------------------------------------------------------------------------
 // ptxas decides per KERNEL, from static instruction counts, whether integer adds, moves and negations go to the ALU

@@ -610,7 +610,11 @@ BJJ_HD uint32_t decompress_finish(Fr& xm, bool sign, const Fr& u, const Fr& vinv
     fr_mul(a, u, vinv);
     if (fr_is_zero(a)) return BJJ_ST_NOT_SQUARE;     // modsqrt rejects a == 0 (src/utils.rs:118)
     Fr w, x0, b, t;
+#if BJJ_POW_SCHED
+    fr_pow_sched(w, a, BJJ_POW_TM1H, BJJ_POW_TM1H_STEPS, BJJ_POW_TM1H_TAIL);
+#else
     fr_pow(w, a, BJJ_EXP_TM1H, BJJ_EXP_TM1H_BITS);
+#endif
     fr_mul(x0, a, w);
     fr_mul(b, x0, w);
     uint32_t k[4];

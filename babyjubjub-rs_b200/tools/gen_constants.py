@@ -254,6 +254,49 @@ def poseidon_grouped_eval(inputs, group=POSEIDON_GROUP):
     return x[0]
 
 
+# ---- fixed exponents: sliding-window schedules ------------------------------------------------------
+# a^e for a PUBLIC exponent, left to right with a window of 4 bits over the odd powers a, a^3, .., a^15: every step is
+# "square n times, multiply by a^(2 idx + 1)"; the first step only selects its power.  For Q - 2 (Fermat inversion) that
+# is 254 squarings + 8 + ~50 multiplications instead of 254 + 126; for (T - 1) / 2 (the square root) 225 + 8 + ~45
+# instead of 225 + 99.
+POW_WINDOW = 4
+
+
+def pow_schedule(e, w=POW_WINDOW):
+    bits = bin(e)[2:]
+    steps, i, pending = [], 0, 0
+    while i < len(bits):
+        if bits[i] == "0":
+            pending += 1
+            i += 1
+            continue
+        j = min(i + w, len(bits))
+        while bits[j - 1] == "0":
+            j -= 1
+        val = int(bits[i:j], 2)
+        steps.append((pending + (j - i), (val - 1) // 2))
+        pending = 0
+        i = j
+    return steps, pending
+
+
+def pow_schedule_eval(a, e):
+    """evaluates a^e mod Q the way csrc/fr.cuh::fr_pow_sched walks the schedule"""
+    steps, tail = pow_schedule(e)
+    a2 = a * a % Q
+    tab = [a % Q]
+    for _ in range((1 << (POW_WINDOW - 1)) - 1):
+        tab.append(tab[-1] * a2 % Q)
+    acc = tab[steps[0][1]]
+    for nsq, idx in steps[1:]:
+        for _ in range(nsq):
+            acc = acc * acc % Q
+        acc = acc * tab[idx] % Q
+    for _ in range(tail):
+        acc = acc * acc % Q
+    return acc
+
+
 # ---- emit ---------------------------------------------------------------------------------------
 def limbs(x):
     assert 0 <= x < (1 << 256)
@@ -306,6 +349,14 @@ def emit(out):
     w("BJJ_CONST uint32_t BJJ_EXP_QM2[8] = %s;\n" % fmt(Q - 2))
     w("BJJ_CONST uint32_t BJJ_EXP_TM1H[8] = %s;   // (T-1)/2, %d bits\n" % (fmt((T - 1) // 2), ((T - 1) // 2).bit_length()))
     w("#define BJJ_EXP_TM1H_BITS %d\n\n" % ((T - 1) // 2).bit_length())
+    w("#define BJJ_POW_TABLE %d   // odd powers a, a^3, .. kept by fr_pow_sched\n" % (1 << (POW_WINDOW - 1)))
+    for name, e in (("QM2", Q - 2), ("TM1H", (T - 1) // 2)):
+        steps, tail = pow_schedule(e)
+        assert all(n < 256 for n, _ in steps) and pow_schedule_eval(3, e) == pow(3, e, Q)
+        w("// a^%s: %d steps of (squarings, index of the odd power), then %d squarings: %d squarings, %d multiplications\n"
+          % (name, len(steps), tail, sum(n for n, _ in steps[1:]) + tail, len(steps) - 1 + (1 << (POW_WINDOW - 1))))
+        w("#define BJJ_POW_%s_STEPS %d\n#define BJJ_POW_%s_TAIL %d\n" % (name, len(steps), name, tail))
+        w("BJJ_CONST uint8_t BJJ_POW_%s[%d][2] = {%s};\n\n" % (name, len(steps), ",".join("{%d,%d}" % st for st in steps)))
 
     # 2-adic part of the square root: g = 5^T generates the order-2^28 subgroup.
     g = pow(5, T, Q)

@@ -58,7 +58,8 @@ def mac(mul, sqr=0):
     return mul * FMUL + sqr * FSQR
 
 
-FERMAT = (126, 254)                                    # fr_inv: a^(Q-2), plain binary: 254 squarings, 126 multiplications
+FERMAT = (56, 253)                                     # fr_inv: a^(Q-2), sliding window of 4 bits (fr_pow_sched): 56 M + 253 S
+SQRT_POW = (49, 224)                                   # a^((T-1)/2) of the square root, same method: 49 M + 224 S
 ALGO_OPS = {
     # k_verify_hash besides Poseidon: two on-curve gates (2 squarings + 3 multiplications each) + 6 Montgomery conversions
     "verify_hash_extra": (6 + 6, 4),
@@ -70,9 +71,9 @@ ALGO_OPS = {
     "fixed_base": (17 * 7 + 1 + 5 + 2 + FERMAT[0] / 32, FERMAT[1] / 32),
     # gate (2S + 3M), conversions, 9-entry table, 64 windows x (4 doublings + 1 addition), batched inversion share
     "mul_scalar": (3 + 4 + 2 + 64 + 7 + 64 * (13 + 7) + 5 + FERMAT[0] / 32, 2 + 64 * 16 + FERMAT[1] / 32),
-    # decompress_point: y^2, d y^2; batched inversion (3 + Fermat / 32); x^2 = u / v; a^((T-1)/2) plain binary over a
-    # 225-bit exponent of weight 99; x0, b; Pohlig-Hellman 21 + 14 + 7 squarings and 8 multiplications; x0^2; 3 conversions
-    "decompress": (1 + 3 + FERMAT[0] / 32 + 1 + 99 + 2 + 8 + 3, 1 + FERMAT[1] / 32 + 225 + 42 + 1),
+    # decompress_point: y^2, d y^2; batched inversion (3 + Fermat / 32); x^2 = u / v; a^((T-1)/2) over a 225-bit
+    # exponent; x0, b; Pohlig-Hellman 21 + 14 + 7 squarings and 8 multiplications; x0^2; 3 conversions
+    "decompress": (1 + 3 + FERMAT[0] / 32 + 1 + SQRT_POW[0] + 2 + 8 + 3, 1 + FERMAT[1] / 32 + SQRT_POW[1] + 42 + 1),
     # PointProjective::add, literal add-2008-bbjlp as src/lib.rs:88-131 sequences it (12 multiplications + 1 squaring) + 9 conversions
     "proj_add": (12 + 9, 1),
 }
@@ -113,7 +114,7 @@ KERNEL_MAC = {
     "k_fixed_base": mac(17 * 7 + 3),
     "k_public": mac(17 * 7 + 3),
     "k_mul_scalar(": mac(3 + 4 + 2 + 64 + 7 + 64 * 20 + 2, 2 + 64 * 16),
-    "k_decompress_finish": mac(1 + 1 + 99 + 2 + 8 + 2, 225 + 42 + 1),
+    "k_decompress_finish": mac(1 + 1 + SQRT_POW[0] + 2 + 8 + 2, SQRT_POW[1] + 42 + 1),
 }
 # Measured on B200 (profiles/r1_pipe_probe.jsonl): IMAD.WIDE.U32 issues at 32 lanes/clk/SM -- half the 32-bit IMAD
 # rate that SURVEY.md section 8d's model (64 lanes/clk/SM) assumes.

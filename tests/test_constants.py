@@ -72,3 +72,19 @@ def test_grouped_poseidon_schedule_equals_dense():
     for t in range(2, 8):
         for K, row in g.poseidon_groups(t):
             assert len(row) == 2 * K * t + K * (K - 1) // 2
+
+
+def test_fixed_exponent_schedules():
+    """the sliding-window schedules of fr_pow_sched (Fermat inversion, square-root exponent) compute the plain powers, and
+    bench.py counts their multiplications and squarings as generated"""
+    import random
+    import bench
+    g = _gen()
+    rnd = random.Random(11)
+    t = (Q - 1) >> 28
+    for name, e, counted in (("QM2", Q - 2, bench.FERMAT), ("TM1H", (t - 1) // 2, bench.SQRT_POW)):
+        for a in (0, 1, 2, Q - 1, rnd.randrange(Q), rnd.randrange(Q)):
+            assert g.pow_schedule_eval(a, e) == pow(a, e, Q), name
+        steps, tail = g.pow_schedule(e)
+        assert all(0 <= idx < 8 and 0 < n < 256 for n, idx in steps)
+        assert counted == (len(steps) - 1 + 7, sum(n for n, _ in steps[1:]) + tail + 1), name
