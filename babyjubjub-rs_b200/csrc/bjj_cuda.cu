@@ -163,6 +163,7 @@ struct bjj_ctx {
     unsigned long long launches;
     cudaError_t last;
     bool verify_split;          // half-size scalars in verify (split.cuh); BJJ_VERIFY_SPLIT=0 turns it off
+    bool sign_fused;            // BJJ_SIGN_FUSED=1: sign as ONE kernel (k_sign) instead of the pipeline of launch_sign
     size_t lane_hint;           // host flavour: the largest chunk of the running call, so that lane-sized scratch is
                                 // allocated ONCE up front (a cudaFree in mid-pipeline is a device-wide synchronisation)
 };
@@ -390,6 +391,8 @@ int bjj_init(int device, bjj_ctx** out) {
     {
         const char* e = getenv("BJJ_VERIFY_SPLIT");
         ctx->verify_split = !(e && e[0] == '0');
+        e = getenv("BJJ_SIGN_FUSED");
+        ctx->sign_fused = e && e[0] == '1';
     }
 #define INIT_CU(call)                  \
     do {                               \
@@ -700,6 +703,44 @@ static int launch_poseidon(bjj_ctx* ctx, int n_inputs, size_t n, const uint8_t* 
     DEV_EPILOGUE
 }
 
+// PrivateKey::sign as a pipeline: k_sign_scalars (BLAKE-512 twice: sk, r) -> R8 = r * B8 and A = sk * B8 on the
+// fixed-base kernels with batched inversions -> hm = Poseidon(R8, A, msg) on k_poseidon<6> -> k_sign_finish (S).  The
+// fused k_sign (one lane start to finish in one thread: 244 registers with spills, a Fermat inversion per lane, 67 % of
+// the multiplier pipe) stays available as BJJ_SIGN_FUSED=1; the pipeline reuses kernels that run at 84-92 %.
+static int launch_sign(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, uint8_t* r8y, uint8_t* s32,
+                       uint8_t* status, cudaStream_t st, Workspace* ws) {
+    if (ctx->sign_fused) {
+        bjjk::sign(grid_cap(ctx, bjjk::sign_blocks_per_sm(), n), st, n, key32, msg32, r8x, r8y, s32, status, ctx->comb);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        return BJJ_OK;
+    }
+    for (size_t off = 0; off < n; off += BJJ_POINT_SUBBATCH) {
+        const size_t m = (n - off) < BJJ_POINT_SUBBATCH ? (n - off) : BJJ_POINT_SUBBATCH;
+        const size_t o = 32 * off;
+        uint8_t *hm, *pts;
+        int rc = ensure_vscratch(ctx, ws, n > BJJ_POINT_SUBBATCH ? BJJ_POINT_SUBBATCH : m, &hm, &pts);
+        if (rc) return rc;
+        const size_t L = 32 * ws->vs_lanes;
+        uint8_t *sk = hm + L, *r = hm + 2 * L, *msgc = hm + 3 * L, *apx = pts, *apy = pts + L;
+        const int grid_s = grid_for(ctx, (const void*)k_scalar_key, m);      // same block size and shape of work
+        bjjk::sign_scalars(grid_s, st, m, key32 + o, msg32 + o, sk, r, msgc, status + off);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        rc = launch_fixed_base(ctx, m, r, r8x + o, r8y + o, false, st, ws);
+        if (rc) return rc;
+        rc = launch_fixed_base(ctx, m, sk, apx, apy, false, st, ws);
+        if (rc) return rc;
+        const uint8_t* ins[5] = {r8x + o, r8y + o, apx, apy, msgc};
+        rc = launch_poseidon(ctx, 5, m, ins, hm, st);
+        if (rc) return rc;
+        bjjk::sign_finish(grid_s, st, m, hm, sk, r, status + off, r8x + o, r8y + o, s32 + o);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return BJJ_OK;
+}
+
 extern "C" {
 
 int bjj_fr_op_batch_dev(bjj_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, void* stream) {
@@ -765,8 +806,7 @@ int bjj_sign_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8
                        uint8_t* s32, uint8_t* status, void* stream) {
     DEV_PROLOGUE
     if (!key32 || !msg32 || !r8x || !r8y || !s32 || !status) return BJJ_ERR_ARG;
-    bjjk::sign(grid_cap(ctx, bjjk::sign_blocks_per_sm(), n), st, n, key32, msg32, r8x, r8y, s32, status, ctx->comb);
-    DEV_EPILOGUE
+    return launch_sign(ctx, n, key32, msg32, r8x, r8y, s32, status, st, &ctx->ws);
 }
 
 int bjj_scalar_key_batch_dev(bjj_ctx* ctx, size_t n, const uint8_t* key32, uint8_t* scalar32, void* stream) {
@@ -1030,8 +1070,7 @@ int bjj_sign_batch(bjj_ctx* ctx, size_t n, const uint8_t* key32, const uint8_t* 
     if (!ctx) return BJJ_ERR_ARG;
     HostArg args[] = {H_IN(key32, 32), H_IN(msg32, 32), H_OUT(r8x, 32), H_OUT(r8y, 32), H_OUT(s32, 32), H_OUT(status, 1)};
     return run_host(ctx, n, args, 6, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
-        bjjk::sign(grid_cap(ctx, bjjk::sign_blocks_per_sm(), m), sl.stream, m, d[0], d[1], d[2], d[3], d[4], d[5], ctx->comb);
-        CHECK_LAUNCH(ctx)
+        return launch_sign(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], sl.stream, &sl.ws);
     });
 }
 

@@ -74,6 +74,10 @@ void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_
 void reduce_scalars(int grid, cudaStream_t st, size_t n, const uint8_t* wide, int k_words, uint8_t* out32);
 void sign(int grid, cudaStream_t st, size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* r8x, uint8_t* r8y,
           uint8_t* s32, uint8_t* status, const bjj::CombEntry* comb);
+void sign_scalars(int grid, cudaStream_t st, size_t n, const uint8_t* key, const uint8_t* msg, uint8_t* sk, uint8_t* r, uint8_t* msgc,
+                  uint8_t* status);
+void sign_finish(int grid, cudaStream_t st, size_t n, const uint8_t* hm, const uint8_t* sk, const uint8_t* r, const uint8_t* status,
+                 uint8_t* r8x, uint8_t* r8y, uint8_t* s32);
 void poseidon(int t, int grid, cudaStream_t st, size_t n, PoseidonIn in, uint8_t* out, uint32_t* gflags);
 
 }  // namespace bjjk

@@ -779,15 +779,12 @@ BJJ_HD void mod_suborder(uint32_t* out, const uint32_t* x, int nwords) {
 // PrivateKey::sign (src/lib.rs:308-342).  status: 0 ok, 4 = "msg outside the Finite Field" (:310).
 //   h = BLAKE512(key); r = BLAKE512(h[32..64] || msg_le32) mod SUBORDER; R8 = B8*r; A = public();
 //   hm = Poseidon(R8.x, R8.y, A.x, A.y, msg);  S = (r + hm * (scalar_key << 3)) mod SUBORDER
-BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, const uint32_t* msg,
-                          const CombEntry* comb, Fr& r8x_m, Fr& r8y_m) {
-    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
-    if (u256_lt(q, msg)) return BJJ_ST_MSG_RANGE;
+// the two scalars of a signature: sk = scalar_key(key), r = BLAKE512(h[32..64] || msg_le32) mod SUBORDER
+BJJ_HD void sign_scalars(uint32_t* sk, uint32_t* r, const uint32_t* key, const uint32_t* msg) {
     uint64_t le[4], h[8], m2[8], h2[8];
 #pragma unroll
     for (int i = 0; i < 4; i++) le[i] = (uint64_t)key[2 * i] | ((uint64_t)key[2 * i + 1] << 32);
     blake512_short<4>(h, le);
-    uint32_t sk[8];
     scalar_key_from_digest(sk, h);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -795,7 +792,7 @@ BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, co
         m2[4 + i] = bswap64((uint64_t)msg[2 * i] | ((uint64_t)msg[2 * i + 1] << 32));   // msg, 32 LE bytes
     }
     blake512_short_be<8>(h2, m2);
-    uint32_t rw[16], r[8];
+    uint32_t rw[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) {          // the 64 digest bytes read as a little-endian integer
         uint64_t l = bswap64(h2[i]);
@@ -803,6 +800,47 @@ BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, co
         rw[2 * i + 1] = (uint32_t)(l >> 32);
     }
     mod_suborder(r, rw, 16);
+}
+
+// S = (r + hm * (sk << 3)) mod SUBORDER, hm the canonical integer of the hash
+BJJ_HD void sign_finish(uint32_t* s_out, const uint32_t* hm, const uint32_t* sk, const uint32_t* r) {
+    // prod = hm * (sk << 3) + r   (8 x 9 limbs -> 17 limbs)
+    uint32_t sk8[9], prod[18];
+    sk8[0] = sk[0] << 3;
+#pragma unroll
+    for (int i = 1; i < 8; i++) sk8[i] = (sk[i] << 3) | (sk[i - 1] >> 29);
+    sk8[8] = sk[7] >> 29;
+#pragma unroll
+    for (int i = 0; i < 18; i++) prod[i] = 0;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            c += (uint64_t)hm[i] * sk8[j] + prod[i + j];
+            prod[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        prod[i + 9] = (uint32_t)c;
+    }
+    uint64_t c = 0;
+#pragma unroll 1
+    for (int i = 0; i < 18; i++) {
+        c += (uint64_t)prod[i] + (i < 8 ? r[i] : 0u);
+        prod[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    mod_suborder(s_out, prod, 18);
+}
+
+// One lane start to finish (the host test harness and the fused k_sign; the library's bjj_sign_batch runs the same
+// steps as a pipeline of kernels, see bjj_cuda.cu::launch_sign).
+BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, const uint32_t* msg,
+                          const CombEntry* comb, Fr& r8x_m, Fr& r8y_m) {
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    if (u256_lt(q, msg)) return BJJ_ST_MSG_RANGE;
+    uint32_t sk[8], r[8];
+    sign_scalars(sk, r, key, msg);
     fixed_base_comb(r8, comb, r);
     PointExt a;
     fixed_base_comb(a, comb, sk);
@@ -834,36 +872,51 @@ BJJ_HD uint32_t sign_core(PointExt& r8, uint32_t* s_out, const uint32_t* key, co
     poseidon_permute<6>(st);
     Fr hm;
     fr_from_mont(hm, st[0]);
-    // prod = hm * (sk << 3) + r   (8 x 9 limbs -> 17 limbs)
-    uint32_t sk8[9], prod[18];
-    sk8[0] = sk[0] << 3;
-#pragma unroll
-    for (int i = 1; i < 8; i++) sk8[i] = (sk[i] << 3) | (sk[i - 1] >> 29);
-    sk8[8] = sk[7] >> 29;
-#pragma unroll
-    for (int i = 0; i < 18; i++) prod[i] = 0;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        uint64_t c = 0;
-#pragma unroll 1
-        for (int j = 0; j < 9; j++) {
-            c += (uint64_t)hm.v[i] * sk8[j] + prod[i + j];
-            prod[i + j] = (uint32_t)c;
-            c >>= 32;
-        }
-        prod[i + 9] = (uint32_t)c;
-    }
-    uint64_t c = 0;
-#pragma unroll 1
-    for (int i = 0; i < 18; i++) {
-        c += (uint64_t)prod[i] + (i < 8 ? r[i] : 0u);
-        prod[i] = (uint32_t)c;
-        c >>= 32;
-    }
-    mod_suborder(s_out, prod, 18);
+    sign_finish(s_out, hm.v, sk, r);
     r8x_m = r8a.x;
     r8y_m = r8a.y;
     return BJJ_ST_OK;
+}
+
+// ---- the same signature as a pipeline (bjj_cuda.cu::launch_sign) -----------------------------------------------
+// phase 1: status, the two scalars, and a copy of msg that is 0 where msg is out of range (so that the Poseidon kernel
+// neither hashes nor flags it)
+BJJ_HD void lane_sign_scalars(const uint8_t* key32, const uint8_t* msg32, uint8_t* sk_out, uint8_t* r_out, uint8_t* msg_out,
+                              uint8_t* status, size_t i) {
+    uint32_t key[8], msg[8], sk[8], r[8];
+    load_u256(key, key32, i);
+    load_u256(msg, msg32, i);
+    const uint32_t q[8] = BJJ_LIMBS8(BJJ_Q);
+    const bool bad = u256_lt(q, msg), eq_q = u256_eq(q, msg);
+    sign_scalars(sk, r, key, msg);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        sk[k] = bad ? 0u : sk[k];
+        r[k] = bad ? 0u : r[k];
+        msg[k] = (bad || eq_q) ? 0u : msg[k];        // msg == Q is accepted and hashes as 0 (Fr::from_str reduces it)
+    }
+    store_u256(sk_out, i, sk);
+    store_u256(r_out, i, r);
+    store_u256(msg_out, i, msg);
+    status[i] = bad ? (uint8_t)BJJ_ST_MSG_RANGE : (uint8_t)BJJ_ST_OK;
+}
+// last phase: S from the hash; rejected lanes return zeros like the fused lane
+BJJ_HD void lane_sign_finish(const uint8_t* hm32, const uint8_t* sk32, const uint8_t* r32, const uint8_t* status, uint8_t* r8x,
+                             uint8_t* r8y, uint8_t* s32, size_t i) {
+    uint32_t hm[8], sk[8], r[8], s[8];
+    if (status[i] != BJJ_ST_OK) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = 0;
+        store_u256(r8x, i, s);
+        store_u256(r8y, i, s);
+        store_u256(s32, i, s);
+        return;
+    }
+    load_u256(hm, hm32, i);
+    load_u256(sk, sk32, i);
+    load_u256(r, r32, i);
+    sign_finish(s, hm, sk, r);
+    store_u256(s32, i, s);
 }
 
 BJJ_HD void lane_sign(const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, uint8_t* r8y, uint8_t* s32,

@@ -809,8 +809,8 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
                     "value": rate, "unit": "hashes/s", "ms_per_step": ms,
                     "roofline_frac_imad": rate * pmac / imad_peak, "oracle_checked_lanes": 128})
 
-    # PrivateKey::sign (next row f-3): BLAKE-512 x2, two fixed-base multiplications (2 x 17 x 7 fmul), ONE shared
-    # Fermat inversion for the two affine conversions, Poseidon, S
+    # PrivateKey::sign (next row f-3) as a pipeline of kernels: BLAKE-512 x2 -> two fixed-base multiplications with
+    # batched inversions -> Poseidon t = 6 -> S
     ns = 1 << 19
     o = [torch.empty((ns, 32), dtype=torch.uint8, device=dev) for _ in range(3)]
     sst = torch.empty(ns, dtype=torch.uint8, device=dev)
@@ -820,7 +820,7 @@ def run_secondaries(args, eng, torch, dev, stream, common, sig):
     assert all(np.array_equal(o[k][:256].cpu().numpy(), er[k]) for k in range(3)), "sign_batch parity"
     rate = ns / (ms * 1e-3)
     out.append({"metric": "signatures_per_sec", "workload": "sign_batch: 2^19 (key, msg) pairs", "value": rate, "unit": "signatures/s",
-                "ms_per_step": ms, "roofline_frac_imad": rate * (mac(2 * 17 * 7 + 12 + 10 + FERMAT[0], FERMAT[1]) + POSEIDON6_MAC) / imad_peak,
+                "ms_per_step": ms, "roofline_frac_imad": rate * (2 * ALGO_MAC["fixed_base"] + poseidon_mac(6, 60, 5)) / imad_peak,
                 "oracle_checked_lanes": 256})
 
     # verify_schnorr (next row f-4): the verify pipeline with full-width scalars (64-65 windows)

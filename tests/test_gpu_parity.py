@@ -1,4 +1,5 @@
 """GPU parity through the C ABI (libbjj_cuda.so) against the oracle.  Bit-exact: this is integer work."""
+import os
 import numpy as np
 import pytest
 
@@ -429,3 +430,26 @@ def test_wide_scalars_match_the_reference_bigint_semantics(gpu):
     oks = bjj.verify_batch([bjj.Point(*pk)] * 2, [bjj.Signature(bjj.Point(*r8), s + (O.SUBORDER << 270)),
                                                     bjj.Signature(bjj.Point(*r8), s + (1 << 256))], [msg, msg])
     assert oks == [True, O.verify(pk, (r8, s + (1 << 256)), msg)]
+
+
+def test_alternative_paths_selected_by_environment(oracle_c):
+    """the paths a context selects at bjj_init from the environment stay bit-exact: verify WITHOUT the half-size scalars
+    (BJJ_VERIFY_SPLIT=0: EdDSA through the 64-window Straus pass) and sign as ONE fused kernel (BJJ_SIGN_FUSED=1)
+    instead of the pipeline of kernels"""
+    from common import Gpu
+    old = {k: os.environ.get(k) for k in ("BJJ_VERIFY_SPLIT", "BJJ_SIGN_FUSED")}
+    os.environ["BJJ_VERIFY_SPLIT"] = "0"
+    os.environ["BJJ_SIGN_FUSED"] = "1"
+    try:
+        alt = Gpu(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    try:
+        parity.check_verify(alt, oracle_c, 32)
+        parity.check_sign(alt, oracle_c, 64)
+    finally:
+        alt.eng.close()
