@@ -164,6 +164,7 @@ struct bjj_ctx {
     cudaError_t last;
     bool verify_split;          // half-size scalars in verify (split.cuh); BJJ_VERIFY_SPLIT=0 turns it off
     bool sign_fused;            // BJJ_SIGN_FUSED=1: sign as ONE kernel (k_sign) instead of the pipeline of launch_sign
+    bool public_fused;          // BJJ_PUBLIC_FUSED=1: PrivateKey::public as ONE kernel (k_public) instead of k_scalar_key + k_fixed_base
     size_t lane_hint;           // host flavour: the largest chunk of the running call, so that lane-sized scratch is
                                 // allocated ONCE up front (a cudaFree in mid-pipeline is a device-wide synchronisation)
 };
@@ -393,6 +394,8 @@ int bjj_init(int device, bjj_ctx** out) {
         ctx->verify_split = !(e && e[0] == '0');
         e = getenv("BJJ_SIGN_FUSED");
         ctx->sign_fused = e && e[0] == '1';
+        e = getenv("BJJ_PUBLIC_FUSED");
+        ctx->public_fused = e && e[0] == '1';
     }
 #define INIT_CU(call)                  \
     do {                               \
@@ -515,10 +518,18 @@ static int launch_fixed_base(bjj_ctx* ctx, size_t n, const uint8_t* in, uint8_t*
         unsigned long long* work = nullptr;
         rc = claim_counter(ctx, ws, st, &work);
         if (rc) return rc;
-        if (from_keys)
+        if (from_keys && ctx->public_fused) {
             k_public<<<grid_for(ctx, (const void*)k_public, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb, work);
-        else
+        } else if (from_keys) {
+            // BLAKE-512 is ALU-only work with an 80 KB body: in its own kernel it neither drags the multiplier kernel's
+            // instruction supply nor makes ptxas put integer adds on the multiplier pipe.  The scalars pass through the
+            // scratch plane that only the batched inversion (afterwards) uses.
+            k_scalar_key<<<grid_for(ctx, (const void*)k_scalar_key, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr.p);
+            ctx->launches++;
+            k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, st>>>(m, scr.p, scr, ctx->comb, work);
+        } else {
             k_fixed_base<<<grid_for(ctx, (const void*)k_fixed_base, m), BJJ_BLOCK, 0, st>>>(m, in + o, scr, ctx->comb, work);
+        }
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         k_batch_affine<<<affine_grid(ctx, m), BJJ_BLOCK, 0, st>>>(m, scr, rx + o, ry + o);

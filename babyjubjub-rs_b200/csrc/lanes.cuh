@@ -756,19 +756,27 @@ BJJ_HD void lane_poseidon(const uint8_t* const* in, uint8_t* out, size_t i, uint
     store_fr(out, i, st[0]);
 }
 
-// x (nwords 32-bit limbs) mod SUBORDER by shift-and-subtract, MSB first.  Signer-side only (two
-// reductions per signature), so clarity wins over speed.
+// x (nwords <= 24 32-bit limbs) mod SUBORDER, canonical.  x = x0 + x1 R + x2 R^2 with R = 2^256: each part is brought
+// below 2l by one Montgomery product with R, R^2, R^3 mod l (split.cuh::montmul_suborder: a * b / R mod l), the sum is
+// below 6l < 2^254 and three conditional subtractions (4l, 2l, l) finish.  (The signer reduces the 512-bit nonce hash
+// and the 576-bit r + hm * 8 sk; a bit-serial shift-and-subtract here cost 14 % of a signature.)
 BJJ_HD void mod_suborder(uint32_t* out, const uint32_t* x, int nwords) {
-    uint32_t acc[8], t[8];
+    uint32_t part[8], acc[8], t[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0;
 #pragma unroll 1
-    for (int bit = nwords * 32 - 1; bit >= 0; bit--) {
-        // acc < l < 2^251, so acc*2 + b fits
+    for (int p = 0; p < 3; p++) {
+        if (8 * p >= nwords) break;
 #pragma unroll
-        for (int i = 7; i > 0; i--) acc[i] = (acc[i] << 1) | (acc[i - 1] >> 31);
-        acc[0] = (acc[0] << 1) | ((x[bit >> 5] >> (bit & 31)) & 1u);
-        uint32_t borrow = sub256(t, acc, BJJ_SUBORDER);
+        for (int i = 0; i < 8; i++) part[i] = (8 * p + i < nwords) ? x[8 * p + i] : 0u;
+        montmul_suborder(t, part, p == 0 ? BJJ_L_R1 : (p == 1 ? BJJ_L_R2 : BJJ_L_R3));
+        add256(acc, acc, t);
+    }
+#pragma unroll 1
+    for (int k = 2; k >= 0; k--) {          // acc -= (l << k) where that keeps it non-negative
+        uint32_t lk[8];
+        u256_shl(lk, BJJ_SUBORDER, k);
+        uint32_t borrow = sub256(t, acc, lk);
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] = borrow ? acc[i] : t[i];
     }

@@ -341,6 +341,8 @@ def emit(out):
     # Montgomery arithmetic modulo l = SUBORDER (verify's half-size scalar split)
     w("#define BJJ_L_NINV32 0x%08xu   // -l^-1 mod 2^32\n" % ((-pow(SUBORDER, -1, 1 << 32)) % (1 << 32)))
     w("BJJ_CONST uint32_t BJJ_L_R2[8] = %s;   // 2^512 mod l\n" % fmt(pow(2, 512, SUBORDER)))
+    w("BJJ_CONST uint32_t BJJ_L_R1[8] = %s;   // 2^256 mod l\n" % fmt(pow(2, 256, SUBORDER)))
+    w("BJJ_CONST uint32_t BJJ_L_R3[8] = %s;   // 2^768 mod l\n" % fmt(pow(2, 768, SUBORDER)))
     w("\n")
 
     # exponent bits for Fermat inversion (Q-2) and sqrt ((T-1)/2 with Q-1 = 2^28*T)

@@ -435,11 +435,12 @@ def test_wide_scalars_match_the_reference_bigint_semantics(gpu):
 def test_alternative_paths_selected_by_environment(oracle_c):
     """the paths a context selects at bjj_init from the environment stay bit-exact: verify WITHOUT the half-size scalars
     (BJJ_VERIFY_SPLIT=0: EdDSA through the 64-window Straus pass) and sign as ONE fused kernel (BJJ_SIGN_FUSED=1)
-    instead of the pipeline of kernels"""
+    instead of the pipeline of kernels, public keys through the fused k_public (BJJ_PUBLIC_FUSED=1)"""
     from common import Gpu
-    old = {k: os.environ.get(k) for k in ("BJJ_VERIFY_SPLIT", "BJJ_SIGN_FUSED")}
+    old = {k: os.environ.get(k) for k in ("BJJ_VERIFY_SPLIT", "BJJ_SIGN_FUSED", "BJJ_PUBLIC_FUSED")}
     os.environ["BJJ_VERIFY_SPLIT"] = "0"
     os.environ["BJJ_SIGN_FUSED"] = "1"
+    os.environ["BJJ_PUBLIC_FUSED"] = "1"
     try:
         alt = Gpu(0)
     finally:
@@ -451,5 +452,6 @@ def test_alternative_paths_selected_by_environment(oracle_c):
     try:
         parity.check_verify(alt, oracle_c, 32)
         parity.check_sign(alt, oracle_c, 64)
+        parity.check_fixed_base(alt, oracle_c, 64)
     finally:
         alt.eng.close()
