@@ -3,7 +3,7 @@
 # Usage (on a GPU box):  bash babyjubjub-rs_b200/tools/sanitize.sh <out-dir>
 out=${1:-gpurun_out/sanitize}
 mkdir -p "$out"
-sel="test_verify or test_mul_scalar or test_split or test_schnorr or test_sign or test_fixed_base or test_wide or test_empty"
+sel="test_verify or test_mul_scalar or test_split or test_schnorr or test_sign or test_fixed_base or test_wide or test_empty or test_compress_decompress or test_poseidon or test_alternative"
 for tool in memcheck racecheck synccheck initcheck; do
   echo "== compute-sanitizer --tool $tool" | tee "$out/$tool.txt"
   timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests -m gpu -x -q -k "$sel" >> "$out/$tool.txt" 2>&1
