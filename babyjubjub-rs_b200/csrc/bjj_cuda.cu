@@ -15,6 +15,12 @@
 using namespace bjj;
 
 #define BJJ_PIPE_SLOTS 2
+
+// integer environment knob (experiments and A/B runs; every default is the measured best)
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
 #define BJJ_CHUNK_LANES (1u << 20)
 #define BJJ_CHUNK_RAMP_LANES ((size_t)1 << 18)   // first chunk of a long host call (see run_host)
 
@@ -133,7 +139,8 @@ struct Workspace {
     unsigned long long* claim;      // BJJ_CLAIM_SLOTS lane-claim counters of the point kernels, handed out round-robin
     unsigned claim_next;
     cudaStream_t aux;        // side stream: the exact-lane kernel overlaps the fast EC kernel
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t aux2;       // second side stream: the exact lanes' late (mop-up) launch, see launch_verify
+    cudaEvent_t ev_fork, ev_fork2, ev_join2, ev_join;
 };
 
 // one of the two staging buffers of the host-pointer flavour: a copy stream, a device arena, and the events that
@@ -207,8 +214,9 @@ static int ensure_table(bjj_ctx* ctx, Workspace* ws, size_t slots) {
 
 // makes room for two queues of n lane indices each and zeroes both counters on `st`
 static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, ExactQueue* q, ExactQueue* q2 = nullptr) {
-    // 32 bytes: the two queue counters, then (at byte 16) the two lane-claim counters of the verify kernels
-    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, 32));
+    // 48 bytes: the two queue counters, then (at byte 16) the lane-claim counters of the verify kernels (hash, Straus)
+    // and (at byte 32) the claim counter of the exact-lane kernels
+    if (!ws->exact_count) CU(ctx, cudaMalloc(&ws->exact_count, 48));
     if (n < ctx->lane_hint) n = ctx->lane_hint;
     if (ws->exact_cap < n) {
         if (ws->exact_list) cudaFree(ws->exact_list);
@@ -217,7 +225,7 @@ static int ensure_queue(bjj_ctx* ctx, Workspace* ws, size_t n, cudaStream_t st, 
         CU(ctx, cudaMalloc(&ws->exact_list, 2 * n * sizeof(uint32_t)));
         ws->exact_cap = n;
     }
-    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, 32, st));
+    CU(ctx, cudaMemsetAsync(ws->exact_count, 0, 48, st));
     q->count = ws->exact_count;
     q->list = ws->exact_list;
     if (q2) {
@@ -271,7 +279,10 @@ static int affine_grid(bjj_ctx* ctx, size_t n) {
 static int ensure_aux(bjj_ctx* ctx, Workspace* ws) {
     if (ws->aux) return BJJ_OK;
     CU(ctx, cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamCreateWithFlags(&ws->aux2, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&ws->ev_fork2, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&ws->ev_join2, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming));
     return BJJ_OK;
 }
@@ -279,9 +290,13 @@ static int ensure_aux(bjj_ctx* ctx, Workspace* ws) {
 static void free_workspace(Workspace* ws) {
     if (ws->aux) {
         cudaStreamSynchronize(ws->aux);
+        cudaStreamSynchronize(ws->aux2);
         cudaEventDestroy(ws->ev_fork);
+        cudaEventDestroy(ws->ev_fork2);
+        cudaEventDestroy(ws->ev_join2);
         cudaEventDestroy(ws->ev_join);
         cudaStreamDestroy(ws->aux);
+        cudaStreamDestroy(ws->aux2);
     }
     if (ws->table) cudaFree(ws->table);
     if (ws->proj) cudaFree(ws->proj);
@@ -612,23 +627,42 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
                           qa, qr, ctx->flags_dev, mode, ctx->verify_split, msg_status ? msg_status + off : nullptr, work_counters(ws));
         ctx->launches++;
         CU(ctx, cudaGetLastError());
+        // The queues are complete after the hash kernel, and the exact lanes (rare; one long ladder each, ~4 % of the
+        // step's multiplier work in the benchmark mix) need nothing else.  They are released in two launches that share
+        // one claim counter:  EARLY, before the split and the Straus kernel, exact_ctas CTAs per SM, so that those few
+        // CTAs are resident first and the Straus CTAs fill the rest of each SM;  LATE, issued behind the Straus kernel
+        // with a full grid, which only finds work when the queues are long (adversarial input).  Measured on one GPU
+        // (profiles/r2_ab_exact_early_chunks.txt): Straus + exact lanes take 59.1 ms per 2^21 lanes either way -- the
+        // multiplier pipe is the shared limit, co-residency does not create throughput -- but the call no longer ends
+        // on a 3-4 ms tail of a few latency-bound warps, which is what the host flavour's last chunk exposes.
+        // All kernels write disjoint ok[] lanes.  BJJ_EXACT_EARLY=0: the late launch alone (round 1's arrangement).
+        static const int exact_early = env_int("BJJ_EXACT_EARLY", 1);
+        static const int exact_ctas = env_int("BJJ_EXACT_CTAS", 2);
+        unsigned long long* exact_work = work_counters(ws) + 2;
+        if (exact_early) {
+            CU(ctx, cudaEventRecord(ws->ev_fork, st));
+            CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+            bjjk::verify_exact(ctx->sms * (exact_ctas < 1 ? 1 : exact_ctas), ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr,
+                               ctx->comb, mode, exact_work);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+        }
         if (ctx->verify_split && mode == BJJ_MODE_EDDSA) {
             bjjk::verify_split(grid_cap(ctx, bjjk::verify_split_blocks_per_sm(), m), st, m, s + o, 1, 0, hm, ws->vs_lanes, ok + off);
             ctx->launches++;
             CU(ctx, cudaGetLastError());
         }
         if (phase_timing) cudaEventRecord(pe[1], st);
-        // the queues are complete.  The Straus kernel goes first so that its CTAs are placed first; the
-        // (slow, rare) exact lanes follow on the side stream in single-warp CTAs that fit next to it.  All
-        // three kernels write disjoint ok[] lanes.
-        CU(ctx, cudaEventRecord(ws->ev_fork, st));
+        CU(ctx, cudaEventRecord(ws->ev_fork2, st));
         bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, ax + o, ay + o, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, mode, work_counters(ws) + 1);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
-        bjjk::verify_exact(ctx->sms * 8, ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr, ctx->comb, mode);
+        CU(ctx, cudaStreamWaitEvent(ws->aux2, ws->ev_fork2, 0));
+        bjjk::verify_exact(ctx->sms * 8, ws->aux2, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr, ctx->comb, mode, exact_work);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(ws->ev_join2, ws->aux2));
+        CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_join2, 0));
         CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
         if (phase_timing) cudaEventRecord(pe[2], st);
         // defer_join: the caller orders whatever consumes ok[] after ws->ev_join itself, and the stream moves on
@@ -889,15 +923,25 @@ struct HostArg {
 // the copies by events.  Chunk sizes ramp up (2^18, 2^19, BJJ_CHUNK_LANES) so that only the first, small
 // host-to-device copy is exposed.
 template <class Launch>
-static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch launch) {
+static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch launch, bool heavy = false) {
     if (!ctx) return BJJ_ERR_ARG;
     for (int a = 0; a < nargs; a++)
         if (!args[a].in && !args[a].out) return BJJ_ERR_ARG;
     if (n == 0) return BJJ_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    const size_t chunk = n < BJJ_CHUNK_LANES ? n : BJJ_CHUNK_LANES;
-    // a chunk may grow by half when the lanes left over after it would make a short, inefficient last chunk
-    const size_t cap = chunk + chunk / 2;
+    // Chunk shape.  Every chunk boundary costs the tails of its kernels (the last wave of the Straus kernel alone is
+    // ~2.5 ms), so the compute-heavy calls (`heavy`: verify*, mul_scalar* -- tens of ns of arithmetic per lane against
+    // ~4 ns of PCIe) go from the small first chunk straight to chunks of 2^21 lanes: the copy of a chunk eight times
+    // larger still ends before the kernels of the one before it.  The copy-bound calls keep the gentle ramp and the
+    // smaller chunk, whose last copy-out is the exposed part.  BJJ_CHUNK_LOG2 / BJJ_CHUNK_GROWTH override (A/B runs).
+    static const int env_log2 = env_int("BJJ_CHUNK_LOG2", 0), env_growth = env_int("BJJ_CHUNK_GROWTH", 0);
+    const size_t chunk_max = env_log2 >= 16 && env_log2 <= 24 ? (size_t)1 << env_log2 : (heavy ? BJJ_POINT_SUBBATCH : (size_t)BJJ_CHUNK_LANES);
+    const size_t growth = env_growth >= 2 ? (size_t)env_growth : (heavy ? 8 : 2);
+    const size_t chunk = n < chunk_max ? n : chunk_max;
+    // a chunk may grow by half when the lanes left over after it would make a short, inefficient last chunk -- but not
+    // past the sub-batch of the point kernels, which would split it into two sets of launches again
+    size_t cap = chunk + chunk / 2;
+    if (cap > BJJ_POINT_SUBBATCH && chunk <= BJJ_POINT_SUBBATCH) cap = BJJ_POINT_SUBBATCH;
     // every array slice starts 256-byte aligned inside the arena
     size_t need = 0;
     for (int a = 0; a < nargs; a++) need += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
@@ -921,7 +965,7 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
     }
     size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
     size_t m = 0;
-    for (size_t off = 0; off < n; off += m, which ^= 1, cur = (2 * cur < chunk ? 2 * cur : chunk)) {
+    for (size_t off = 0; off < n; off += m, which ^= 1, cur = (growth * cur < chunk ? growth * cur : chunk)) {
         PipeSlot& sl = ctx->slot[which];
         m = (n - off) < cur ? (n - off) : cur;
         if (n - off - m < cur / 2 && n - off <= cap) m = n - off;      // fold a short remainder into this chunk
@@ -1048,7 +1092,7 @@ int bjj_mul_scalar_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar32, 32), H_OUT(rx, 32), H_OUT(ry, 32)};
     return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_mul_scalar(ctx, m, d[0], d[1], d[2], 8, d[3], d[4], sl.stream, &sl.ws);
-    });
+    }, /*heavy=*/true);
 }
 
 int bjj_mul_scalar_wide_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* scalar, int scalar_words,
@@ -1057,7 +1101,7 @@ int bjj_mul_scalar_wide_batch(bjj_ctx* ctx, size_t n, const uint8_t* px, const u
     HostArg args[] = {H_IN(px, 32), H_IN(py, 32), H_IN(scalar, (size_t)4 * scalar_words), H_OUT(rx, 32), H_OUT(ry, 32)};
     return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_mul_scalar(ctx, m, d[0], d[1], d[2], scalar_words, d[3], d[4], sl.stream, &sl.ws);
-    });
+    }, /*heavy=*/true);
 }
 
 int bjj_fixed_base_batch(bjj_ctx* ctx, size_t n, const uint8_t* scalar32, uint8_t* rx, uint8_t* ry) {
@@ -1127,7 +1171,7 @@ int bjj_verify_batch(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8_t* 
     HostArg args[] = {H_IN(r8x, 32), H_IN(r8y, 32), H_IN(s32, 32), H_IN(ax, 32), H_IN(ay, 32), H_IN(msg32, 32), H_OUT(ok, 1)};
     return run_host(ctx, n, args, 7, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_verify(ctx, m, d[0], d[1], d[2], d[3], d[4], d[5], d[6], sl.stream, &sl.ws, BJJ_MODE_EDDSA, nullptr, true);
-    });
+    }, /*heavy=*/true);
 }
 
 int bjj_verify_schnorr_batch(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const uint8_t* pky, const uint8_t* msg32,
@@ -1137,7 +1181,7 @@ int bjj_verify_schnorr_batch(bjj_ctx* ctx, size_t n, const uint8_t* pkx, const u
                       H_OUT(status, 1)};
     return run_host(ctx, n, args, 8, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_verify(ctx, m, d[3], d[4], d[5], d[0], d[1], d[2], d[6], sl.stream, &sl.ws, BJJ_MODE_SCHNORR, d[7], true);
-    });
+    }, /*heavy=*/true);
 }
 
 int bjj_verify_compressed_batch(bjj_ctx* ctx, size_t n, const uint8_t* sig64, const uint8_t* pk32,
@@ -1146,7 +1190,7 @@ int bjj_verify_compressed_batch(bjj_ctx* ctx, size_t n, const uint8_t* sig64, co
     HostArg args[] = {H_IN(sig64, 64), H_IN(pk32, 32), H_IN(msg32, 32), H_OUT(ok, 1), H_OUT(status, 1)};
     return run_host(ctx, n, args, 5, [&](size_t m, uint8_t** d, ComputeRef sl) -> int {
         return launch_verify_compressed(ctx, m, d[0], d[1], d[2], d[3], d[4], sl.stream, &sl.ws);
-    });
+    }, /*heavy=*/true);
 }
 
 }  // extern "C"

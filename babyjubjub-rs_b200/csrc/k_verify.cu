@@ -18,6 +18,9 @@ using namespace bjj;
 #define BJJ_VERIFY_HASH_MINB 2
 #endif
 #define BJJ_VERIFY_EXACT_BLOCK 64
+#ifndef BJJ_VERIFY_EXACT_REGS
+#define BJJ_VERIFY_EXACT_REGS 232      // 64 x 232 registers fit beside four Straus CTAs (4 x 128 x 96) on one SM
+#endif
 
 #if BJJ_VERIFY_HASH_MINB > 0
 __global__ void __launch_bounds__(BJJ_BLOCK, BJJ_VERIFY_HASH_MINB) k_verify_hash(
@@ -161,19 +164,27 @@ __global__ void __launch_bounds__(BJJ_VM_THREADS, BJJ_EC_VM_MINB) k_verify_ec_vm
 }
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
-// One launch serves both queues: the first half of the grid takes the "A off the curve" queue, the second
-// half the "only R8 off the curve" queue, so no warp ever mixes the two ladders.
-__global__ void __launch_bounds__(BJJ_VERIFY_EXACT_BLOCK) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
+// A warp claims 32 queue entries at a time from `work` -- first the "A off the curve" queue (the longer ladder), then the
+// "only R8 off the curve" queue, so no warp ever mixes the two ladders -- until both are exhausted.  Several launches
+// may share one counter (bjj_cuda.cu::launch_verify: a small early grid beside the Straus kernel, a full late one).
+__global__ void __maxnreg__(BJJ_VERIFY_EXACT_REGS) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                                          uint8_t* ok, ExactQueue qa, ExactQueue qr,
-                                                                         const CombEntry* comb, int mode) {
-    const uint32_t half = gridDim.x / 2;
-    if (blockIdx.x < half) {
-        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, cnt = *qa.count; j < cnt; j += half * blockDim.x)
-            lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb, mode);
-    } else {
-        for (uint32_t j = (blockIdx.x - half) * blockDim.x + threadIdx.x, cnt = *qr.count; j < cnt; j += half * blockDim.x)
-            lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb, mode);
+                                                                         const CombEntry* comb, int mode, unsigned long long* work) {
+    const uint32_t ca = *qa.count, cr = *qr.count, lane = threadIdx.x & 31;
+    const unsigned long long ua = (ca + 31u) >> 5, total = ua + ((cr + 31u) >> 5);
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(work, 1ull);
+        u = __shfl_sync(0xFFFFFFFFu, u, 0);
+        if (u >= total) break;
+        if (u < ua) {
+            const uint32_t j = (uint32_t)u * 32 + lane;
+            if (j < ca) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb, mode);
+        } else {
+            const uint32_t j = (uint32_t)(u - ua) * 32 + lane;
+            if (j < cr) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb, mode);
+        }
     }
 }
 
@@ -222,8 +233,8 @@ void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const ui
 }
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, ExactQueue qa, ExactQueue qr, const CombEntry* comb,
-                  int mode) {
-    k_verify_exact<<<grid & ~1, BJJ_VERIFY_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, hm, ok, qa, qr, comb, mode);
+                  int mode, unsigned long long* work) {
+    k_verify_exact<<<grid, BJJ_VERIFY_EXACT_BLOCK, 0, st>>>(r8x, r8y, s, ax, ay, hm, ok, qa, qr, comb, mode, work);
 }
 
 }  // namespace bjjk

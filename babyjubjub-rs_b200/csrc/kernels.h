@@ -66,7 +66,7 @@ void verify_ec(int grid, cudaStream_t st, size_t n, const uint8_t* r8x, const ui
                const bjj::CombEntry* comb, int mode, unsigned long long* work);
 void verify_exact(int grid, cudaStream_t st, const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s, const uint8_t* ax,
                   const uint8_t* ay, const uint8_t* hm, uint8_t* ok, bjj::ExactQueue qa, bjj::ExactQueue qr,
-                  const bjj::CombEntry* comb, int mode);
+                  const bjj::CombEntry* comb, int mode, unsigned long long* work);
 void mul_scalar(int grid, cudaStream_t st, size_t n, const uint8_t* px, const uint8_t* py, const uint8_t* k,
                 bjj::ProjScratch scr, bjj::U128* table, bjj::ExactQueue q, uint32_t* gflags);
 void mul_scalar_exact(int grid, cudaStream_t st, const uint8_t* px, const uint8_t* py, const uint8_t* k, int k_words, uint8_t* rx,
