@@ -139,8 +139,7 @@ struct Workspace {
     unsigned long long* claim;      // BJJ_CLAIM_SLOTS lane-claim counters of the point kernels, handed out round-robin
     unsigned claim_next;
     cudaStream_t aux;        // side stream: the exact-lane kernel overlaps the fast EC kernel
-    cudaStream_t aux2;       // second side stream: the exact lanes' late (mop-up) launch, see launch_verify
-    cudaEvent_t ev_fork, ev_fork2, ev_join2, ev_join;
+    cudaEvent_t ev_fork, ev_join;
 };
 
 // one of the two staging buffers of the host-pointer flavour: a copy stream, a device arena, and the events that
@@ -150,6 +149,14 @@ struct PipeSlot {
     uint8_t* arena;
     size_t arena_bytes;
     cudaEvent_t ev_in, ev_out;
+    // pageable caller arrays (what a plain Vec<u8> / malloc gives): page-locked mirror of the arena, same layout.  The
+    // calling thread copies a chunk's inputs in while the GPU works on the chunk before, and copies a chunk's outputs
+    // out ("drain") when the slot comes round again -- a cudaMemcpyAsync on pageable memory would block it instead.
+    uint8_t* hstage;
+    size_t hstage_bytes;
+    cudaEvent_t ev_done;       // after the slot's device-to-host copies
+    bool drain_pending;
+    size_t drain_off, drain_lanes;
 };
 // what a launch runs on
 struct ComputeRef {
@@ -279,10 +286,7 @@ static int affine_grid(bjj_ctx* ctx, size_t n) {
 static int ensure_aux(bjj_ctx* ctx, Workspace* ws) {
     if (ws->aux) return BJJ_OK;
     CU(ctx, cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking));
-    CU(ctx, cudaStreamCreateWithFlags(&ws->aux2, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
-    CU(ctx, cudaEventCreateWithFlags(&ws->ev_fork2, cudaEventDisableTiming));
-    CU(ctx, cudaEventCreateWithFlags(&ws->ev_join2, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming));
     return BJJ_OK;
 }
@@ -290,13 +294,9 @@ static int ensure_aux(bjj_ctx* ctx, Workspace* ws) {
 static void free_workspace(Workspace* ws) {
     if (ws->aux) {
         cudaStreamSynchronize(ws->aux);
-        cudaStreamSynchronize(ws->aux2);
         cudaEventDestroy(ws->ev_fork);
-        cudaEventDestroy(ws->ev_fork2);
-        cudaEventDestroy(ws->ev_join2);
         cudaEventDestroy(ws->ev_join);
         cudaStreamDestroy(ws->aux);
-        cudaStreamDestroy(ws->aux2);
     }
     if (ws->table) cudaFree(ws->table);
     if (ws->proj) cudaFree(ws->proj);
@@ -382,6 +382,8 @@ void bjj_destroy(bjj_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int s = 0; s < BJJ_PIPE_SLOTS; s++) {
         if (ctx->slot[s].arena) cudaFree(ctx->slot[s].arena);
+        if (ctx->slot[s].hstage) cudaFreeHost(ctx->slot[s].hstage);
+        if (ctx->slot[s].ev_done) cudaEventDestroy(ctx->slot[s].ev_done);
         if (ctx->slot[s].ev_in) cudaEventDestroy(ctx->slot[s].ev_in);
         if (ctx->slot[s].ev_out) cudaEventDestroy(ctx->slot[s].ev_out);
         if (ctx->slot[s].stream) cudaStreamDestroy(ctx->slot[s].stream);
@@ -430,6 +432,7 @@ int bjj_init(int device, bjj_ctx** out) {
         INIT_CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
         INIT_CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_in, cudaEventDisableTiming));
         INIT_CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_out, cudaEventDisableTiming));
+        INIT_CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_done, cudaEventDisableTiming));
     }
     INIT_CU(cudaMalloc(&ctx->flags_dev, sizeof(uint32_t)));
     INIT_CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(uint32_t), ctx->stream));
@@ -628,24 +631,29 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         // The queues are complete after the hash kernel, and the exact lanes (rare; one long ladder each, ~4 % of the
-        // step's multiplier work in the benchmark mix) need nothing else.  They are released in two launches that share
-        // one claim counter:  EARLY, before the split and the Straus kernel, exact_ctas CTAs per SM, so that those few
-        // CTAs are resident first and the Straus CTAs fill the rest of each SM;  LATE, issued behind the Straus kernel
-        // with a full grid, which only finds work when the queues are long (adversarial input).  Measured on one GPU
-        // (profiles/r2_ab_exact_early_chunks.txt): Straus + exact lanes take 59.1 ms per 2^21 lanes either way -- the
-        // multiplier pipe is the shared limit, co-residency does not create throughput -- but the call no longer ends
-        // on a 3-4 ms tail of a few latency-bound warps, which is what the host flavour's last chunk exposes.
-        // All kernels write disjoint ok[] lanes.  BJJ_EXACT_EARLY=0: the late launch alone (round 1's arrangement).
+        // step's multiplier work in the benchmark mix) need nothing else: their kernel is released HERE, on the side
+        // stream, before the split and the Straus kernel.  Its CTAs are placed first; those that find the queues empty
+        // leave at once and the Straus CTAs move into the SMs as they free up (both kernels claim their work
+        // dynamically), so the ladders are out of the way early instead of forming a 3-4 ms tail of a few
+        // latency-bound warps at the end of the call.  Measured on one GPU (profiles/r2_ab_exact_early_chunks.txt), per
+        // 2^21 lanes: 89.5 ms against 90.4 ms with the exact kernel behind the Straus kernel (BJJ_EXACT_EARLY=0, round
+        // 1's arrangement).  A small early grid beside the Straus CTAs does not help: the multiplier pipe is the
+        // shared limit, Straus + exact take 59.1 ms however they overlap.  All kernels write disjoint ok[] lanes.
         static const int exact_early = env_int("BJJ_EXACT_EARLY", 1);
-        static const int exact_ctas = env_int("BJJ_EXACT_CTAS", 2);
-        unsigned long long* exact_work = work_counters(ws) + 2;
-        if (exact_early) {
+        static const int exact_ctas = env_int("BJJ_EXACT_CTAS", 8);
+        auto launch_exact = [&]() -> int {
             CU(ctx, cudaEventRecord(ws->ev_fork, st));
             CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
             bjjk::verify_exact(ctx->sms * (exact_ctas < 1 ? 1 : exact_ctas), ws->aux, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr,
-                               ctx->comb, mode, exact_work);
+                               ctx->comb, mode, work_counters(ws) + 2);
             ctx->launches++;
             CU(ctx, cudaGetLastError());
+            CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
+            return BJJ_OK;
+        };
+        if (exact_early) {
+            rc = launch_exact();
+            if (rc) return rc;
         }
         if (ctx->verify_split && mode == BJJ_MODE_EDDSA) {
             bjjk::verify_split(grid_cap(ctx, bjjk::verify_split_blocks_per_sm(), m), st, m, s + o, 1, 0, hm, ws->vs_lanes, ok + off);
@@ -653,17 +661,13 @@ static int launch_verify(bjj_ctx* ctx, size_t n, const uint8_t* r8x, const uint8
             CU(ctx, cudaGetLastError());
         }
         if (phase_timing) cudaEventRecord(pe[1], st);
-        CU(ctx, cudaEventRecord(ws->ev_fork2, st));
         bjjk::verify_ec(grid_e, st, m, r8x + o, r8y + o, ax + o, ay + o, hm, ws->vs_lanes, ok + off, ws->table, ctx->comb, mode, work_counters(ws) + 1);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
-        CU(ctx, cudaStreamWaitEvent(ws->aux2, ws->ev_fork2, 0));
-        bjjk::verify_exact(ctx->sms * 8, ws->aux2, r8x + o, r8y + o, s + o, ax + o, ay + o, hm, ok + off, qa, qr, ctx->comb, mode, exact_work);
-        ctx->launches++;
-        CU(ctx, cudaGetLastError());
-        CU(ctx, cudaEventRecord(ws->ev_join2, ws->aux2));
-        CU(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_join2, 0));
-        CU(ctx, cudaEventRecord(ws->ev_join, ws->aux));
+        if (!exact_early) {
+            rc = launch_exact();
+            if (rc) return rc;
+        }
         if (phase_timing) cudaEventRecord(pe[2], st);
         // defer_join: the caller orders whatever consumes ok[] after ws->ev_join itself, and the stream moves on
         // to the next batch while the (latency-bound) exact lanes finish beside it
@@ -918,10 +922,12 @@ struct HostArg {
 
 // Copies and kernels overlap, kernels never overlap each other: every kernel of this library is sized to fill
 // the GPU and streams a large instruction footprint, and two of them sharing SMs starve each other's
-// instruction fetch (measured: two concurrent verify pipelines ran at 0.65x the serial rate).  So the two slots
+// instruction fetch (measured: two concurrent verify pipelines ran at 0.65x the serial rate; round 2, odd chunks on a
+// second compute stream so that the block scheduler could fill one chunk's kernel tails with the next chunk's
+// kernels: 17.8 against 22.7 M verifies/s end to end, profiles/r2_ab_exact_early_chunks.txt).  So the two slots
 // only own copy streams and staging arenas; all launches go to the context's one compute stream, ordered against
-// the copies by events.  Chunk sizes ramp up (2^18, 2^19, BJJ_CHUNK_LANES) so that only the first, small
-// host-to-device copy is exposed.
+// the copies by events.  Chunk sizes ramp up from 2^18 lanes so that only the first, small host-to-device copy is
+// exposed (shape: see below).
 template <class Launch>
 static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch launch, bool heavy = false) {
     if (!ctx) return BJJ_ERR_ARG;
@@ -929,6 +935,19 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         if (!args[a].in && !args[a].out) return BJJ_ERR_ARG;
     if (n == 0) return BJJ_OK;
     CU(ctx, cudaSetDevice(ctx->device));
+    // Which caller arrays are pageable?  (cudaHostAlloc'd / cudaHostRegister'ed ones go to the copy engine directly.)
+    static const int stage_pageable = env_int("BJJ_STAGE_PAGEABLE", 1);
+    bool staged[16];
+    bool any_staged = false;
+    for (int a = 0; a < nargs; a++) {
+        cudaPointerAttributes at;
+        const void* hp = args[a].in ? (const void*)args[a].in : (const void*)args[a].out;
+        const cudaError_t e = cudaPointerGetAttributes(&at, hp);
+        if (e != cudaSuccess) cudaGetLastError();
+        staged[a] = stage_pageable && (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered);
+        any_staged = any_staged || staged[a];
+    }
+    for (int k = 0; k < BJJ_PIPE_SLOTS; k++) ctx->slot[k].drain_pending = false;      // (an aborted call may have left one)
     // Chunk shape.  Every chunk boundary costs the tails of its kernels (the last wave of the Straus kernel alone is
     // ~2.5 ms), so the compute-heavy calls (`heavy`: verify*, mul_scalar* -- tens of ns of arithmetic per lane against
     // ~4 ns of PCIe) go from the small first chunk straight to chunks of 2^21 lanes: the copy of a chunk eight times
@@ -936,7 +955,9 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
     // smaller chunk, whose last copy-out is the exposed part.  BJJ_CHUNK_LOG2 / BJJ_CHUNK_GROWTH override (A/B runs).
     static const int env_log2 = env_int("BJJ_CHUNK_LOG2", 0), env_growth = env_int("BJJ_CHUNK_GROWTH", 0);
     const size_t chunk_max = env_log2 >= 16 && env_log2 <= 24 ? (size_t)1 << env_log2 : (heavy ? BJJ_POINT_SUBBATCH : (size_t)BJJ_CHUNK_LANES);
-    const size_t growth = env_growth >= 2 ? (size_t)env_growth : (heavy ? 8 : 2);
+    // (staged, i.e. pageable, arrays: the calling thread's memcpy of the next chunk, ~20 ns per verify lane, has to fit
+    // under the kernels of this one, ~43 ns per lane -- so those calls double instead)
+    const size_t growth = env_growth >= 2 ? (size_t)env_growth : (heavy && !any_staged ? 8 : 2);
     const size_t chunk = n < chunk_max ? n : chunk_max;
     // a chunk may grow by half when the lanes left over after it would make a short, inefficient last chunk -- but not
     // past the sub-batch of the point kernels, which would split it into two sets of launches again
@@ -963,6 +984,19 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         cudaEventCreate(&t0);
         cudaEventRecord(t0, ctx->stream);
     }
+    // copies a drained slot's outputs from its page-locked mirror to the caller's (pageable) arrays
+    auto drain = [&](PipeSlot& sl) -> int {
+        if (!sl.drain_pending) return BJJ_OK;
+        CU(ctx, cudaEventSynchronize(sl.ev_done));
+        size_t pos = 0;
+        for (int a = 0; a < nargs; a++) {
+            if (args[a].out && staged[a])
+                memcpy(args[a].out + sl.drain_off * args[a].bytes_per_lane, sl.hstage + pos, sl.drain_lanes * args[a].bytes_per_lane);
+            pos += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
+        }
+        sl.drain_pending = false;
+        return BJJ_OK;
+    };
     size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
     size_t m = 0;
     for (size_t off = 0; off < n; off += m, which ^= 1, cur = (growth * cur < chunk ? growth * cur : chunk)) {
@@ -977,15 +1011,34 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
             CU(ctx, cudaMalloc(&sl.arena, need));
             sl.arena_bytes = need;
         }
+        if (any_staged) {
+            // the slot's previous chunk: its results go out to the caller, and its host-to-device copies have long
+            // finished reading the mirror (they precede ev_done on the slot's stream)
+            rc = drain(sl);
+            if (rc) break;
+            if (sl.hstage_bytes < need) {
+                CU(ctx, cudaStreamSynchronize(sl.stream));
+                if (sl.hstage) cudaFreeHost(sl.hstage);
+                sl.hstage = nullptr;
+                sl.hstage_bytes = 0;
+                CU(ctx, cudaHostAlloc(&sl.hstage, need, cudaHostAllocDefault));
+                sl.hstage_bytes = need;
+            }
+        }
         // the slot's copy stream is ordered: these copies follow the slot's previous results going out
         uint8_t* dptr[16];
         size_t pos = 0;
         for (int a = 0; a < nargs; a++) {
             dptr[a] = sl.arena + pos;
+            if (args[a].in) {
+                const uint8_t* src = args[a].in + off * args[a].bytes_per_lane;
+                if (staged[a]) {
+                    memcpy(sl.hstage + pos, src, m * args[a].bytes_per_lane);
+                    src = sl.hstage + pos;
+                }
+                CU(ctx, cudaMemcpyAsync(dptr[a], src, m * args[a].bytes_per_lane, cudaMemcpyHostToDevice, sl.stream));
+            }
             pos += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
-            if (args[a].in)
-                CU(ctx, cudaMemcpyAsync(dptr[a], args[a].in + off * args[a].bytes_per_lane, m * args[a].bytes_per_lane,
-                                        cudaMemcpyHostToDevice, sl.stream));
         }
         ComputeRef comp{ctx->stream, which ? ctx->ws2 : ctx->ws};
         CU(ctx, cudaEventRecord(sl.ev_in, sl.stream));
@@ -1000,21 +1053,40 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         }
         CU(ctx, cudaStreamWaitEvent(comp.stream, sl.ev_in, 0));
         rc = launch(m, dptr, comp);
-        if (rc) {
-            // copies and kernels of earlier chunks may still be in flight against the caller's buffers: drain them
-            // before handing the buffers back
-            bjj_sync(ctx);
-            return rc;
-        }
+        if (rc) break;
         if (mark) cudaEventRecord(marks[nmarks].comp, comp.stream);
         CU(ctx, cudaEventRecord(sl.ev_out, comp.stream));
         CU(ctx, cudaStreamWaitEvent(sl.stream, sl.ev_out, 0));
         if (comp.ws.aux) CU(ctx, cudaStreamWaitEvent(sl.stream, comp.ws.ev_join, 0));      // deferred exact lanes
-        for (int a = 0; a < nargs; a++)
+        pos = 0;
+        for (int a = 0; a < nargs; a++) {
             if (args[a].out)
-                CU(ctx, cudaMemcpyAsync(args[a].out + off * args[a].bytes_per_lane, dptr[a], m * args[a].bytes_per_lane,
-                                        cudaMemcpyDeviceToHost, sl.stream));
+                CU(ctx, cudaMemcpyAsync(staged[a] ? sl.hstage + pos : args[a].out + off * args[a].bytes_per_lane, dptr[a],
+                                        m * args[a].bytes_per_lane, cudaMemcpyDeviceToHost, sl.stream));
+            pos += ((args[a].bytes_per_lane * cap + 255) & ~(size_t)255);
+        }
+        if (any_staged) {
+            CU(ctx, cudaEventRecord(sl.ev_done, sl.stream));
+            sl.drain_pending = true;
+            sl.drain_off = off;
+            sl.drain_lanes = m;
+        }
         if (mark) cudaEventRecord(marks[nmarks++].out, sl.stream);
+    }
+    if (rc) {
+        // copies and kernels of earlier chunks may still be in flight against the caller's buffers: drain them before
+        // handing the buffers back
+        bjj_sync(ctx);
+        for (int k = 0; k < BJJ_PIPE_SLOTS; k++) ctx->slot[k].drain_pending = false;
+        return rc;
+    }
+    for (int k = 0; k < BJJ_PIPE_SLOTS; k++) {       // oldest first: `which` now names the slot used two chunks ago
+        const int r2 = drain(ctx->slot[which ^ k]);
+        if (r2 && !rc) rc = r2;
+    }
+    if (rc) {
+        bjj_sync(ctx);
+        return rc;
     }
     rc = bjj_sync(ctx);
     if (pipe_timing) {

@@ -19,7 +19,7 @@ using namespace bjj;
 #endif
 #define BJJ_VERIFY_EXACT_BLOCK 64
 #ifndef BJJ_VERIFY_EXACT_REGS
-#define BJJ_VERIFY_EXACT_REGS 232      // 64 x 232 registers fit beside four Straus CTAs (4 x 128 x 96) on one SM
+#define BJJ_VERIFY_EXACT_REGS 240      // four 64-thread CTAs per SM
 #endif
 
 #if BJJ_VERIFY_HASH_MINB > 0
@@ -165,26 +165,27 @@ __global__ void __launch_bounds__(BJJ_VM_THREADS, BJJ_EC_VM_MINB) k_verify_ec_vm
 
 // exact lanes: off-curve inputs replay the reference sequence (rare; fed by the queues of k_verify_hash).
 // A warp claims 32 queue entries at a time from `work` -- first the "A off the curve" queue (the longer ladder), then the
-// "only R8 off the curve" queue, so no warp ever mixes the two ladders -- until both are exhausted.  Several launches
-// may share one counter (bjj_cuda.cu::launch_verify: a small early grid beside the Straus kernel, a full late one).
+// "only R8 off the curve" queue, so no warp ever mixes the two ladders -- until both are exhausted.
 __global__ void __maxnreg__(BJJ_VERIFY_EXACT_REGS) k_verify_exact(const uint8_t* r8x, const uint8_t* r8y, const uint8_t* s,
                                                                          const uint8_t* ax, const uint8_t* ay, const uint8_t* hm,
                                                                          uint8_t* ok, ExactQueue qa, ExactQueue qr,
                                                                          const CombEntry* comb, int mode, unsigned long long* work) {
     const uint32_t ca = *qa.count, cr = *qr.count, lane = threadIdx.x & 31;
     const unsigned long long ua = (ca + 31u) >> 5, total = ua + ((cr + 31u) >> 5);
-    for (;;) {
+    auto claim = [&]() -> unsigned long long {
         unsigned long long u = 0;
         if (lane == 0) u = atomicAdd(work, 1ull);
-        u = __shfl_sync(0xFFFFFFFFu, u, 0);
-        if (u >= total) break;
-        if (u < ua) {
-            const uint32_t j = (uint32_t)u * 32 + lane;
-            if (j < ca) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb, mode);
-        } else {
-            const uint32_t j = (uint32_t)(u - ua) * 32 + lane;
-            if (j < cr) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb, mode);
-        }
+        return __shfl_sync(0xFFFFFFFFu, u, 0);
+    };
+    unsigned long long u = claim();
+    // one loop per ladder (a unit that ends the first loop is the first of the second)
+    for (; u < ua; u = claim()) {
+        const uint32_t j = (uint32_t)u * 32 + lane;
+        if (j < ca) lane_verify_exact<true>(r8x, r8y, s, ax, ay, hm, ok, qa.list[j], comb, mode);
+    }
+    for (; u < total; u = claim()) {
+        const uint32_t j = (uint32_t)(u - ua) * 32 + lane;
+        if (j < cr) lane_verify_exact<false>(r8x, r8y, s, ax, ay, hm, ok, qr.list[j], comb, mode);
     }
 }
 
