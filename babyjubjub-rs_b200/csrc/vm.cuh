@@ -105,7 +105,15 @@ static __device__ __noinline__ void sqr2(Slot d0, Slot a0, Slot d1, Slot a1) {
     st(d1, r1);
 }
 // d = a + b, d = a - b (lazy domain [0, 2Q))
+// (BJJ_VM_FAKE_SMALL_OPS: timing experiment only -- the additions and subtractions return at once, results are wrong;
+//  it bounds what fusing them into the multiplication subroutines could gain, profiles/r2_ab_exact_early_chunks.txt)
+#ifdef BJJ_VM_FAKE_SMALL_OPS
+#define BJJ_VM_SMALL_OP_BEGIN return;
+#else
+#define BJJ_VM_SMALL_OP_BEGIN
+#endif
 static __device__ __noinline__ void add(Slot d, Slot a, Slot b) {
+    BJJ_VM_SMALL_OP_BEGIN
     Fr x, y, r;
     ld(x, a);
     ld(y, b);
@@ -113,6 +121,7 @@ static __device__ __noinline__ void add(Slot d, Slot a, Slot b) {
     st(d, r);
 }
 static __device__ __noinline__ void sub(Slot d, Slot a, Slot b) {
+    BJJ_VM_SMALL_OP_BEGIN
     Fr x, y, r;
     ld(x, a);
     ld(y, b);
@@ -121,6 +130,7 @@ static __device__ __noinline__ void sub(Slot d, Slot a, Slot b) {
 }
 // both at once: s = a + b, d = a - b (the (Y+X, Y-X) and (H, G) pairs of the curve formulas)
 static __device__ __noinline__ void addsub(Slot s, Slot d, Slot a, Slot b) {
+    BJJ_VM_SMALL_OP_BEGIN
     Fr x, y, r;
     ld(x, a);
     ld(y, b);

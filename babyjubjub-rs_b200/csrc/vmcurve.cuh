@@ -38,6 +38,7 @@ static __device__ __noinline__ void neg(Slot d, Slot a) {
 }
 // d = 2a - b
 static __device__ __noinline__ void dblsub(Slot d, Slot a, Slot b) {
+    BJJ_VM_SMALL_OP_BEGIN
     Fr x, y, r;
     ld(x, a);
     ld(y, b);

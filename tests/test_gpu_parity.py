@@ -248,6 +248,35 @@ def test_device_pointer_flavour_across_subbatches(gpu, oracle_c):
         chk = np.concatenate([bad[:64], bad[-64:], np.arange(16)])
         assert np.array_equal(ok2[chk], oracle_c.verify(host["r8x"][chk], host["r8y"][chk], host["s"][chk], hax[chk],
                                                         host["ay"][chk], hmsg[chk]))
+        # The call above took PAGEABLE numpy arrays: the library staged them through its page-locked mirror.  The same
+        # batch from page-locked arrays (bjj_host_alloc: copied by the DMA engine directly) and from a mix of both must
+        # give the same bytes.
+        cols = [host["r8x"], host["r8y"], host["s"], hax, host["ay"], hmsg]
+        pinned_ptrs = []
+
+        def pinned_like(a):
+            ptr = lib.bjj_host_alloc(a.nbytes)
+            assert ptr
+            pinned_ptrs.append(ptr)
+            v = np.frombuffer((ctypes.c_uint8 * a.nbytes).from_address(ptr), dtype=np.uint8).reshape(a.shape)
+            v[...] = a
+            return v
+        try:
+            pcols = [pinned_like(c) for c in cols]
+            pok = pinned_like(np.zeros(n2, dtype=np.uint8))
+
+            def call(cs, okbuf):
+                okbuf[...] = 7
+                rc = lib.bjj_verify_batch(ctx, n2, *[c.ctypes.data_as(ctypes.c_void_p) for c in cs], okbuf.ctypes.data_as(ctypes.c_void_p))
+                assert rc == 0
+                return okbuf.copy()
+            assert np.array_equal(call(pcols, pok), exp2), "all arrays page-locked"
+            mixed = [pcols[0], cols[1], pcols[2], cols[3], cols[4], pcols[5]]
+            assert np.array_equal(call(mixed, np.empty(n2, dtype=np.uint8)), exp2), "mixed, pageable result"
+            assert np.array_equal(call(cols, pok), exp2), "pageable inputs, page-locked result"
+        finally:
+            for ptr in pinned_ptrs:
+                lib.bjj_host_free(ctypes.c_void_p(ptr))
     finally:
         for p in list(d.values()) + [d_st, d_ok]:
             lib.bjj_dev_free(ctx, p)
