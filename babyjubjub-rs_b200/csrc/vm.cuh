@@ -90,10 +90,21 @@ static __device__ __noinline__ void mul2(Slot d0, Slot a0, Slot b0, Slot d1, Slo
 #ifndef BJJ_VM_SQR
 #define BJJ_VM_SQR 1
 #endif
-static __device__ __noinline__ void sqr2(Slot d0, Slot a0, Slot d1, Slot a1) {
+// pre != 0: d1 = (a1 + b1)^2 -- the (X+Y)^2 of a doubling without a call, a load pair and a store pair for the sum.
+// (The same idea carried further -- Y+-X and the E, F, G, H butterflies formed in the prologue of ONE product pair behind a
+// mode switch, table entries read from global memory inside it -- was built and measured: correct, and no faster, 58.0-58.8
+// against 58.1-58.3 ms per 2^21 lanes for every combination, although a timing-only build with the additions and
+// subtractions EMPTY runs 3.3 ms faster: what they cost is their own carry chains, not the calls, loads and stores around
+// them.  profiles/r2_ab_exact_early_chunks.txt.)
+static __device__ __noinline__ void sqr2(Slot d0, Slot a0, Slot d1, Slot a1, Slot b1, int pre) {
     Fr x0, x1, r0, r1;
     ld(x0, a0);
     ld(x1, a1);
+    if (pre) {
+        Fr t;
+        ld(t, b1);
+        fr_add(x1, x1, t);
+    }
 #if BJJ_VM_SQR
     fr_sqr_inline(r0, x0);
     fr_sqr_inline(r1, x1);

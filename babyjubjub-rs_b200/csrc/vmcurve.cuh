@@ -1,6 +1,6 @@
 // Twisted-Edwards arithmetic (a = -1 model, extended coordinates) over shared-memory slots: the formulas of
 // curve.cuh (ext_dbl, ext_add_niels, ext_add_niels_aff, niels_from_ext) expressed as sequences of the out-of-line
-// operations of vm.cuh.  A doubling is 9 calls, an addition 7; the instruction footprint of a whole Straus pass is
+// operations of vm.cuh.  A doubling is 7 calls, an addition 7; the instruction footprint of a whole Straus pass is
 // a few KB of call sites plus ~10 KB of subroutines, instead of 150 KB of inlined multiplications per window.
 //
 // Reference items: PointProjective::add (src/lib.rs:88-131) and Point::mul_scalar (src/lib.rs:149-164) for inputs ON
@@ -88,9 +88,8 @@ __device__ __forceinline__ void set_identity(const Regs& s) {
 
 // acc = 2 acc   (dbl-2008-hwcd, a = -1: 4S + 3M, +1M for T; curve.cuh::ext_dbl)
 __device__ __forceinline__ void dbl(const Regs& s, bool want_t) {
-    sqr2(s.t0, s.X, s.t1, s.Y);                  // xx, yy
-    add(s.t3, s.X, s.Y);
-    sqr2(s.t2, s.Z, s.t3, s.t3);                 // zz, (X+Y)^2
+    sqr2(s.t0, s.X, s.t1, s.Y, s.Y, 0);          // xx, yy
+    sqr2(s.t2, s.Z, s.t3, s.X, s.Y, 1);          // zz, (X+Y)^2
     addsub(s.t4, s.t1, s.t1, s.t0);              // H' = yy + xx, G = yy - xx
     sub(s.t3, s.t3, s.t4);                       // E = 2XY
     dblsub(s.t2, s.t2, s.t1);                    // F' = 2zz - G
