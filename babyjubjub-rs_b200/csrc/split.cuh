@@ -115,6 +115,32 @@ BJJ_HD void u256_muladd(uint32_t* x, const uint32_t* y, uint32_t q) {
     }
 }
 
+// r = x * a - y * b   (the caller guarantees 0 <= x a - y b < 2^256; x, y < 2^32)
+BJJ_HD void u256_lin_sub(uint32_t* r, uint32_t x, const uint32_t* a, uint32_t y, const uint32_t* b) {
+    uint64_t c1 = 0, c2 = 0;
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c1 += (uint64_t)x * a[i];
+        c2 += (uint64_t)y * b[i];
+        const uint64_t d = (uint64_t)(uint32_t)c1 - (uint32_t)c2 - borrow;
+        r[i] = (uint32_t)d;
+        borrow = (uint32_t)(d >> 63);
+        c1 >>= 32;
+        c2 >>= 32;
+    }
+}
+// r = x * a + y * b   (x, y < 2^31; no overflow of 256 bits)
+BJJ_HD void u256_lin_add(uint32_t* r, uint32_t x, const uint32_t* a, uint32_t y, const uint32_t* b) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)x * a[i] + (uint64_t)y * b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+
 // u, |v| and the sign of v (vneg = 1: v < 0) with  u = v * h (mod l),  v odd,  0 <= u,  0 < |v| < l.
 // h is any 256-bit integer.
 BJJ_HD void split_scalars(uint32_t* u, uint32_t* v, uint32_t& vneg, const uint32_t* h) {
@@ -144,6 +170,62 @@ BJJ_HD void split_scalars(uint32_t* u, uint32_t* v, uint32_t& vneg, const uint32
         const int nb = (B[7] ? 256 - BJJ_CLZ32(B[7]) : u256_bitlen(B)) - s;      // bitlen(b); <= 0 for b == 0
         if (nb <= 126) break;
         const uint32_t bh = B[7];
+#ifndef BJJ_SPLIT_LEHMER
+#define BJJ_SPLIT_LEHMER 1
+#endif
+#if BJJ_SPLIT_LEHMER
+        // Lehmer: run Euclid on the leading words (A[7], B[7]) for as long as the TRUE remainders are certainly
+        // non-negative and still >= 2^126, then apply the accumulated 2x2 cofactor matrix to the long numbers once --
+        // ~8 quotients per multi-precision pass instead of one.  With r_0 = a, r_1 = b the remainders are
+        // r_j = (-1)^j (x_j a - y_j b), x_j, y_j >= 0; cutting a and b to their leading words changes r_j by less than
+        // max(x_j, y_j) units of the leading word, so  r^_j >= x_j + y_j (+ the 2^126 mark in those units)  keeps the
+        // true r_j >= 0 (resp. >= 2^126).  The quotients need not be the true ones: ANY sequence of steps with
+        // non-negative remainders preserves the invariants above, and the pair is re-ordered after the pass.
+        {
+            // true r >= 2^126  <=  (r << s) >= 2^(126+s)  <=  r^ >= 2^(s-98) + error   (r^ in units of 2^224)
+            const uint32_t mark = s > 98 ? (s - 98 >= 32 ? 0xFFFFFFFFu : (1u << (s - 98))) : 1u;
+            uint32_t rp = A[7], rc = bh, x0 = 1, y0 = 0, x1 = 0, y1 = 1;
+            int steps = 0;
+#pragma unroll 1
+            while (rc != 0) {
+                const uint32_t q = rp / rc, rn = rp - q * rc;
+                const uint64_t xn = x0 + (uint64_t)q * x1, yn = y0 + (uint64_t)q * y1;
+                if ((xn | yn) >> 31) break;
+                if ((uint64_t)rn < xn + yn + mark) break;
+                rp = rc;
+                rc = rn;
+                x0 = x1;
+                y0 = y1;
+                x1 = (uint32_t)xn;
+                y1 = (uint32_t)yn;
+                steps++;
+            }
+            if (steps > 0) {
+                // (a, b) <- (r_steps, r_steps+1);  cofactor magnitudes x |ta| + y |tb|;  the signs alternate per step
+                uint32_t na[8], nb2[8], nta[8], ntb[8];
+                if (steps & 1) {
+                    u256_lin_sub(na, y0, B, x0, A);
+                    u256_lin_sub(nb2, x1, A, y1, B);
+                } else {
+                    u256_lin_sub(na, x0, A, y0, B);
+                    u256_lin_sub(nb2, y1, B, x1, A);
+                }
+                u256_lin_add(nta, x0, ta, y0, tb);
+                u256_lin_add(ntb, x1, ta, y1, tb);
+                bneg ^= (uint32_t)(steps & 1);
+                const bool sw = u256_lt(na, nb2);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    A[i] = sw ? nb2[i] : na[i];
+                    B[i] = sw ? na[i] : nb2[i];
+                    ta[i] = sw ? ntb[i] : nta[i];
+                    tb[i] = sw ? nta[i] : ntb[i];
+                }
+                bneg ^= sw ? 1u : 0u;
+                goto renormalise;
+            }
+        }
+#endif
         if (bh == 0) {
             // b is 2^31 times shorter than a (degenerate h): the estimate below would crawl; halve a instead
             split_step_pow2(A, ta, B, tb);
@@ -166,6 +248,9 @@ BJJ_HD void split_scalars(uint32_t* u, uint32_t* v, uint32_t& vneg, const uint32
             bneg ^= 1u;
         }
         // renormalise (A >= B, A != 0: the pair has gcd 1 or l)
+#if BJJ_SPLIT_LEHMER
+    renormalise:
+#endif
 #pragma unroll 1
         while (A[7] == 0) {              // rare: a lost 32 bits or more in one step
 #pragma unroll
