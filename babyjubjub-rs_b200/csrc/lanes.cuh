@@ -132,8 +132,8 @@ BJJ_HD void table_select(Niels& n, const LaneTable& t, int d) {
 // comb[w][j] = j * 65536^w * B8 as affine Niels (y+x, y-x, 2d'xy) on the a = -1 model, j = 0..32768,
 // w = 0..16 (w = 16 only holds j = 0, 1 for the recoding carry): 16 x 32,769 x 96 B = 50 MB, L2-resident,
 // gathered with ld.global.nc.  Built once per context on the device (k_comb_build, ~15 ms).  Signed 16-bit
-// digits make a fixed-base multiplication 17 mixed additions and no doubling; the Straus pass of verify
-// reads window 0 of the same table every fourth radix-16 window.
+// digits make a fixed-base multiplication 17 mixed additions and no doubling; verify adds its B8 term (w * B8, the
+// one full-width scalar left after the split) the same way, after the Straus pass over the two per-lane points.
 #define BJJ_COMB_BITS 16
 #define BJJ_COMB_WINDOWS 17
 #define BJJ_COMB_ENTRIES 32769
@@ -948,8 +948,9 @@ BJJ_HD void lane_sign(const uint8_t* key32, const uint8_t* msg32, uint8_t* r8x, 
 // verify (src/lib.rs:395-412).  Returns 0/1 like the reference's bool.
 //   msg > Q -> false; hm = Poseidon(R8.x, R8.y, A.x, A.y, msg mod Q);
 //   accept iff  S*B8 == R8 + (8*hm)*A   compared in affine coordinates.
-// Fast lane (A and R8 on the curve): 8*hm*A = hm*(8A), so one Straus pass computes
-//   P = S*B8 + hm*(-8A)  and the test is  P == R8  checked projectively (no inversion).
+// Fast lane (A and R8 on the curve): the group equation  S*B8 - R8 - hm*(8A) == O  multiplied by an odd v with
+//   u = v*hm, w = v*S (mod l) half-size (split.cuh): one Straus pass over  u*(-+8A) + |v|*(-R8),  then  + w*B8  from the
+//   comb, and the test is  sum == O = (0 : 1 : 1)  checked projectively (no inversion).
 // Exact lane (any input point off the curve): the reference sequence replayed literally, in a second
 // kernel fed by the ExactQueue.
 // mode selects the signature scheme sharing this pipeline:
