@@ -366,13 +366,25 @@ def split_scalar_inputs(seed=77, n_random=400):
     hs += [(L * pn // qn + d) % (1 << 256) for qn in (2, 3, 5, 7, 64, 1 << 20, (1 << 40) + 1) for pn in (1, qn - 1) for d in (0, 1)]
     hs += [L // k for k in (2, 3, 4, 1 << 31, 1 << 32, (1 << 32) + 1, 1 << 64, 1 << 125, 1 << 126, 1 << 127)]
     hs += [rnd.randrange(1 << b) for b in (8, 31, 32, 33, 64, 100, 125, 126, 127, 128, 129, 160, 192, 224, 250, 251, 252, 254, 256)]
+    # chosen partial-quotient patterns of h / l (the Lehmer batches of the split run the quotient sequence on the leading
+    # words: all-ones = the longest sequence, huge quotients = no step fits a leading word, mixtures = batches that end early)
+
+    def from_cf(qs):
+        num, den = 0, 1
+        for q in reversed(qs):
+            num, den = den, q * den + num
+        return (L * num // den) % (1 << 256)
+    for pattern in ([1] * 200, [2] * 120, [1, 2] * 90, [1, 1 << 15] * 12, [1 << 16] * 16, [(1 << 31) - 1] * 9, [1 << 32] * 8, [3, 1 << 33] * 6,
+                    [1] * 40 + [1 << 20] + [1] * 100, [65535, 1, 65536, 2] * 8, [1] * 73 + [1 << 30, 1 << 30], [255] * 32, [65537] * 15):
+        hs += [(from_cf(pattern) + d) % (1 << 256) for d in (-1, 0, 1)]
+    hs += [((L >> b) << b) % (1 << 256) for b in range(8, 256, 8)] + [(L >> b) + 1 for b in range(1, 256, 5)]
     hs += [rnd.randrange(Q) for _ in range(n_random)]
     ss = [rnd.randrange(1 << 256) for _ in hs]
     ss[0], ss[1], ss[2] = 0, 2**256 - 1, L
     return hs, ss
 
 
-def check_split_outputs(hs, ss, us, vs, negs, ws, max_wide=90):
+def check_split_outputs(hs, ss, us, vs, negs, ws, max_wide=190):
     """the invariants that make the split exact: u = v*h (mod l), v odd and non-zero, w = |v|*s (mod l)"""
     L = SUBORDER_L
     wide = 0
