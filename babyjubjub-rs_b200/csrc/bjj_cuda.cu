@@ -997,7 +997,7 @@ static int run_host(bjj_ctx* ctx, size_t n, HostArg* args, int nargs, Launch lau
         sl.drain_pending = false;
         return BJJ_OK;
     };
-    size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
+    size_t cur = n > 2 * BJJ_CHUNK_RAMP_LANES && chunk > BJJ_CHUNK_RAMP_LANES ? BJJ_CHUNK_RAMP_LANES : chunk;
     size_t m = 0;
     for (size_t off = 0; off < n; off += m, which ^= 1, cur = (growth * cur < chunk ? growth * cur : chunk)) {
         PipeSlot& sl = ctx->slot[which];
