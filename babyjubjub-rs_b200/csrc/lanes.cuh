@@ -294,7 +294,10 @@ BJJ_HD void store_zero_scratch(const ProjScratch& s, size_t i) {
 // (A warp-cooperative variant of the inversion below -- prefix/suffix products across the 32 lanes by shuffles, one
 // Fermat inversion of the warp's total -- was measured and dropped: under SIMT the 32 per-thread inversions of a warp
 // already ARE one instruction stream, so sharing it buys nothing and the 12 extra multiplications cost: public_batch
-// 341 -> 322 M keys/s.  What amortises the inversion is lanes per thread.)
+// 341 -> 322 M keys/s.  What amortises the inversion is lanes per thread.  Two independent product chains per thread,
+// merged before the one inversion, were measured as well: 2.570 against 2.564 ms per 2^20 keys at 32 lanes per thread,
+// 2.61 / 2.88 ms at 64 / 128 lanes per thread -- the kernel lives on the number of resident warps, and lanes per thread
+// take them away.  profiles/r2_ab_exact_early_chunks.txt.)
 BJJ_HD void batch_affine_strided(const ProjScratch& s, uint8_t* rx, uint8_t* ry, size_t n, size_t t, size_t T) {
     const Fr one = fr_const(BJJ_ONE_M);
     Fr acc = one, z;
