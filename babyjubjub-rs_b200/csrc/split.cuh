@@ -90,6 +90,40 @@ BJJ_HD void split_step_pow2(uint32_t* a, uint32_t* ta, const uint32_t* b, const 
     add256(ta, ta, tc);
 }
 
+// One shift-and-subtract step of the division of d by b (d >= b), mirrored on the relation (a, ta):
+// d -= 2^k b, a -= 2^k b, |ta| += 2^k |tb|  with the largest k that keeps d >= 0.
+BJJ_HD void split_step_div(uint32_t* d, uint32_t* a, uint32_t* ta, const uint32_t* b, const uint32_t* tb) {
+    int k = u256_bitlen(d) - u256_bitlen(b);
+    uint32_t c[8], tc[8], t[8], half[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c[i] = b[i];
+        tc[i] = tb[i];
+    }
+#pragma unroll 1
+    for (; k >= 32; k -= 32) {          // whole-limb shifts: degenerate h only
+#pragma unroll
+        for (int i = 7; i > 0; i--) {
+            c[i] = c[i - 1];
+            tc[i] = tc[i - 1];
+        }
+        c[0] = 0;
+        tc[0] = 0;
+    }
+    u256_shl(c, c, k);
+    u256_shl(tc, tc, k);
+    const uint32_t over = sub256(t, d, c);       // borrow: c > d (then the shift was >= 1) and half of c is used
+    u256_shr1(half, c);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = over ? half[i] : c[i];
+    u256_shr1(half, tc);
+#pragma unroll
+    for (int i = 0; i < 8; i++) tc[i] = over ? half[i] : tc[i];
+    sub256(d, d, c);
+    sub256(a, a, c);
+    add256(ta, ta, tc);
+}
+
 // x -= q * y  (x >= q * y)
 BJJ_HD void u256_mulsub(uint32_t* x, const uint32_t* y, uint32_t q) {
     uint64_t carry = 0;
@@ -306,9 +340,19 @@ BJJ_HD void split_scalars(uint32_t* u, uint32_t* v, uint32_t& vneg, const uint32
     // |tb| <= l / a < 2^125.  Otherwise ta is odd (the invariant sum is odd) and stays odd under ta += 2^k tb:
     // phase 2 keeps reducing a by b, without swapping, until a is short too.
     const bool second = !(tb[0] & 1u);
-    if (second) {
+    if (second && !split_small(a)) {
+        // The relations (a - j b, |ta| + j |tb|), j >= 0, all have an odd cofactor.  The smallest j that brings a - j b
+        // under the 32-window limit LIM is  j = floor((a - LIM) / b) + 1  -- it leaves the SMALLEST cofactor among the
+        // short ones (halving a greedily, as the first version did, overshoots j by up to 2x and with it |v|; 3.8 % of
+        // random hm then needed a 33rd window, which its whole warp pays for).  d = a - LIM is divided by b by
+        // shift-and-subtract, every step mirrored on (a, ta); then one more b comes off.
+        uint32_t d[8];
+        const uint32_t lim[8] = {0u, 0u, 0u, 0x70000000u, 0u, 0u, 0u, 0u};
+        sub256(d, a, lim);
 #pragma unroll 1
-        while (!split_small(a)) split_step_pow2(a, ta, b, tb);
+        while (!u256_lt(d, b)) split_step_div(d, a, ta, b, tb);
+        sub256(a, a, b);               // a = LIM + d - b  in (0, LIM)
+        add256(ta, ta, tb);
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
