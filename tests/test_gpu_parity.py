@@ -282,6 +282,54 @@ def test_device_pointer_flavour_across_subbatches(gpu, oracle_c):
             lib.bjj_dev_free(ctx, p)
 
 
+def test_host_flavour_chunk_boundaries(gpu, oracle_c):
+    """bjj_verify_batch / bjj_public_batch from PAGEABLE arrays at sizes around every chunk boundary of the host pipeline
+    (first chunk 2^18, then up to 2^21 for verify and the doubling ramp for public; short remainders are folded into the
+    last chunk): every lane answered, none twice, results as constructed"""
+    import ctypes
+    eng = gpu.eng
+    lib, ctx = eng.lib, eng.ctx
+    nmax = (1 << 21) + (1 << 18) + 5
+    rng = np.random.default_rng(11)
+    keys = rng.integers(0, 256, size=(nmax, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, size=(nmax, 32), dtype=np.uint8)
+    msgs[:, 31] &= 0x1F
+
+    def dev(nbytes):
+        p = lib.bjj_dev_alloc(ctx, nbytes)
+        assert p
+        return ctypes.c_void_p(p)
+    d = {k: dev(32 * nmax) for k in ("keys", "msgs", "r8x", "r8y", "s", "ax", "ay")}
+    d_st = dev(nmax)
+    try:
+        for name, arr in (("keys", keys), ("msgs", msgs)):
+            assert lib.bjj_memcpy_h2d(ctx, d[name], arr.ctypes.data_as(ctypes.c_void_p), 32 * nmax) == 0
+        assert lib.bjj_sign_batch_dev(ctx, nmax, d["keys"], d["msgs"], d["r8x"], d["r8y"], d["s"], d_st, None) == 0
+        assert lib.bjj_public_batch_dev(ctx, nmax, d["keys"], d["ax"], d["ay"], None) == 0
+        host = {}
+        for name in ("r8x", "r8y", "s", "ax", "ay"):
+            host[name] = np.empty((nmax, 32), dtype=np.uint8)
+            assert lib.bjj_memcpy_d2h(ctx, host[name].ctypes.data_as(ctypes.c_void_p), d[name], 32 * nmax) == 0
+        eng.sync()
+    finally:
+        for p in list(d.values()) + [d_st]:
+            lib.bjj_dev_free(ctx, p)
+    bad = np.arange(7, nmax, 65521)
+    host["s"][bad, 1] ^= 2
+    sizes = [(1 << 18) - 1, (1 << 18) + 1, (1 << 19) + 3, 3 * (1 << 18), (1 << 20) + (1 << 17) + 1, (1 << 21) - 1, (1 << 21) + 1,
+             (1 << 21) + (1 << 17), nmax]
+    for n in sizes:
+        ok = eng.verify_batch(host["r8x"][:n], host["r8y"][:n], host["s"][:n], host["ax"][:n], host["ay"][:n], msgs[:n])
+        exp = np.ones(n, dtype=np.uint8)
+        exp[bad[bad < n]] = 0
+        assert ok.shape == (n,) and np.array_equal(ok, exp), n
+    for n in ((1 << 18) + 1, 3 * (1 << 18) + 7, (1 << 20) + (1 << 18) + 1):
+        px, py = eng.public_batch(keys[:n])
+        assert np.array_equal(px, host["ax"][:n]) and np.array_equal(py, host["ay"][:n]), n
+    idx = np.concatenate([np.arange(4), bad[:8], np.arange(nmax - 4, nmax)])
+    assert np.array_equal(exp[idx], oracle_c.verify(host["r8x"][idx], host["r8y"][idx], host["s"][idx], host["ax"][idx], host["ay"][idx], msgs[idx]))
+
+
 def test_config1_bench_workloads_1024(gpu, oracle_c):
     """BASELINE config 1: the criterion workloads of benches/bench_babyjubjub.rs (add, mul_scalar_small,
     mul_scalar, compress, decompress, sign, verify) on a 1,024-element synthetic batch, lane for lane
